@@ -1,0 +1,103 @@
+// Implicit-GEMM convolution / linear layer on tcgen05 tensor cores (sm_100a).
+//
+// One kernel covers every contraction of the UNet and TAESD hot path:
+//   conv3x3 (stride 1/2, pad 1), conv1x1, Linear, fused "conv3x3 + 1x1 shortcut" (longer K loop),
+//   channel-concatenated inputs (several TMA sources, zero-copy torch.cat), split-K.
+// Activations are NHWC fp16; a "row" of the GEMM is one output pixel (or token), a K-block is
+// 64 channels of one filter tap, fetched by a 4-D tiled TMA box whose (h, w) origin is shifted by
+// the tap offset -- out-of-bounds rows are zero-filled by the TMA unit, which is the conv padding.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b2 {
+
+constexpr int IG_BM = 128;        // rows (pixels/tokens) per CTA tile == UMMA M
+constexpr int IG_BK = 64;         // fp16 elements per K-block (128 B = one swizzle row)
+constexpr int IG_MAX_SRC = 3;
+constexpr int IG_MAX_STAGES = 8;
+constexpr int IG_THREADS = 192;   // warp0: TMA, warp1: MMA + TMEM alloc, warps 2-5: epilogue
+
+enum : int {
+    IG_RELU = 1,    // relu after bias/residual
+    IG_GEGLU = 2,   // tile columns [0,BN/2) = value, [BN/2,BN) = gate; out = v * gelu_erf(g)
+    IG_SPLITK = 4,  // write fp32 partials, epilogue applied by igemm_finalize_kernel
+};
+
+struct IgEpilogue {
+    __half* out;            // [rows][ldc] fp16
+    int ldc;
+    const float* colbias;   // fp32 [nb][colbias_bstride]: bias (+ time-embedding projection); may be null
+    int colbias_bstride;    // 0 => shared by every batch item
+    const __half* res;      // residual / noise, same row indexing as out; may be null
+    int ldr;
+    float acc_scale;        // out = acc_scale * (acc + bias) + res_scale * res
+    float res_scale;
+    int flags;
+    int n_valid;            // valid output columns (Cout)
+};
+
+struct IgemmParams {
+    CUtensorMap tmA[IG_MAX_SRC];
+    CUtensorMap tmB;
+    int seg_ntap[IG_MAX_SRC];     // 1 or 9
+    int seg_cblocks[IG_MAX_SRC];  // 64-channel blocks in this segment
+    int seg_c0[IG_MAX_SRC];       // first channel inside the source view
+    int nseg;
+    int total_kb;
+    int kb_per_split;
+    int tw, th, tn;               // output tile = tn images x th rows x tw cols  (<= 128 pixels)
+    int tiles_w, tiles_h, tiles_n;
+    int Wo, Ho, Nb;
+    int stride;                   // input coord = stride * out + tap - 1
+    int BN;                       // UMMA N (multiple of 16, <= 256)
+    int num_stages;
+    uint32_t a_bytes;             // TMA box bytes of one A tile
+    uint32_t b_bytes;
+    uint32_t tmem_cols;
+    float* partial;               // [splits][rows_total][n_pad] fp32 (split-K only)
+    int n_pad;
+    IgEpilogue epi;
+};
+
+struct ActView {
+    const __half* ptr;
+    int N, H, W, C;   // logical NHWC extents visible to the TMA map
+    int ld;           // channel pitch in elements (>= C, multiple of 8)
+};
+
+struct IgemmDesc {
+    ActView src[IG_MAX_SRC];
+    int ntap[IG_MAX_SRC];
+    int nseg;
+    const __half* w;  // packed weights [w_rows][w_ld], K order = segments in sequence, each [tap][c]
+    int w_rows;
+    int w_ld;
+    int stride;
+    int Nb, Ho, Wo;
+    int BN;           // 0 = auto
+    int splits;       // 0/1 = none
+    float* partial;   // workspace for split-K (size splits*rows*n_pad floats)
+    IgEpilogue epi;
+};
+
+struct IgemmPlan {
+    IgemmParams p;
+    dim3 grid;
+    size_t smem;
+    int splits;
+    long rows_total;
+};
+
+// Returns 0 on success; fills plan. Encodes TMA descriptors (host side, no launch).
+int igemm_plan(const IgemmDesc& d, IgemmPlan* plan);
+// Enqueue on stream (main kernel + split-K finalize if needed).
+int igemm_launch(const IgemmPlan& plan, cudaStream_t stream);
+// workspace floats needed for a split-K plan
+size_t igemm_partial_floats(int splits, long rows_total, int n_valid);
+const char* b2_last_error();
+void b2_set_error(const char* fmt, ...);
+
+}  // namespace b2

@@ -1,0 +1,65 @@
+"""ctypes binding of libb200sd.so (include/b200sd.h).  There is no CPU fallback: if the shared
+library is missing or a call fails this module raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libb200sd.so")
+
+
+class B2Error(RuntimeError):
+    pass
+
+
+class ActView(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("c", C.c_int),
+                ("ld", C.c_int)]
+
+
+class IgemmDesc(C.Structure):
+    _fields_ = [
+        ("src", ActView * 3), ("ntap", C.c_int * 3), ("nseg", C.c_int),
+        ("w", C.c_void_p), ("w_rows", C.c_int), ("w_ld", C.c_int), ("stride", C.c_int),
+        ("nb", C.c_int), ("ho", C.c_int), ("wo", C.c_int),
+        ("bn", C.c_int), ("splits", C.c_int), ("partial", C.c_void_p),
+        ("out", C.c_void_p), ("ldc", C.c_int),
+        ("colbias", C.c_void_p), ("colbias_bstride", C.c_int),
+        ("res", C.c_void_p), ("ldr", C.c_int),
+        ("acc_scale", C.c_float), ("res_scale", C.c_float),
+        ("flags", C.c_int), ("n_valid", C.c_int),
+    ]
+
+
+IG_RELU = 1
+IG_GEGLU = 2
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libb200sd.so; fails loudly when it has not been built (python __graft_entry__.py)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B2Error(f"{LIB_PATH} not found: build it with `make -C ai-rtc-agent_b200/csrc` "
+                          "(or __graft_entry__.build()); there is no CPU fallback")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.b2sd_last_error.restype = C.c_char_p
+        _lib.b2sd_version.restype = C.c_int
+        _lib.b2sd_op_igemm.argtypes = [C.POINTER(IgemmDesc), C.c_void_p]
+        _lib.b2sd_op_igemm.restype = C.c_int
+        _lib.b2sd_igemm_partial_floats.argtypes = [C.c_int, C.c_int64, C.c_int]
+        _lib.b2sd_igemm_partial_floats.restype = C.c_uint64
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise B2Error(f"{what}: {lib().b2sd_last_error().decode(errors='replace')}")
+
+
+def current_stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
