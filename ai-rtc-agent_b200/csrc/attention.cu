@@ -1,0 +1,350 @@
+// tcgen05 flash attention (see attention.cuh).
+#include "attention.cuh"
+
+#include <cudaTypedefs.h>
+#include <math.h>
+#include <string.h>
+
+#include "igemm.cuh"  // b2_set_error
+#include "ptx.cuh"
+
+namespace b2 {
+
+constexpr int AT_BQ = 128;      // query rows per CTA == UMMA M
+constexpr int AT_STAGES = 2;    // K/V ring depth
+constexpr int AT_THREADS = 192; // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2-5 softmax
+constexpr uint32_t AT_TMEM_S0 = 0, AT_TMEM_S1 = 128, AT_TMEM_O = 256, AT_TMEM_COLS = 512;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+struct AttnParams {
+    CUtensorMap tmq, tmk, tmv;
+    __half* out;
+    int ldo;
+    int sq, skv, heads, d_real;
+    long k_bstride, vt_bstride;
+    float scale_log2;
+};
+
+template <int DA, int BKV>
+__global__ void __launch_bounds__(AT_THREADS) attn_kernel(const __grid_constant__ AttnParams p) {
+    constexpr int DP = DA * 64;
+    constexpr int KVA = BKV / 64;                       // kv atoms per block (P / V^T tiles)
+    constexpr uint32_t Q_BYTES = DA * AT_BQ * 128;      // DA atoms of [128 rows][128 B]
+    constexpr uint32_t K_BYTES = DA * BKV * 128;        // DA atoms of [BKV rows][128 B]
+    constexpr uint32_t V_BYTES = KVA * DP * 128;        // KVA atoms of [DP rows][128 B]
+    constexpr uint32_t STAGE_BYTES = K_BYTES + V_BYTES;
+    constexpr uint32_t P_BYTES = KVA * AT_BQ * 128;
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sQ = smem;
+    uint8_t* sKV = sQ + Q_BYTES;
+    uint8_t* sP = sKV + AT_STAGES * STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;               // [AT_STAGES]
+    uint64_t* kv_empty = kv_full + AT_STAGES;   // [AT_STAGES]
+    uint64_t* s_full = kv_empty + AT_STAGES;    // [2]
+    uint64_t* s_empty = s_full + 2;             // [2]
+    uint64_t* p_full = s_empty + 2;
+    uint64_t* o_done = p_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * AT_BQ;
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int nblk = (p.skv + BKV - 1) / BKV;
+
+    if (threadIdx.x == 0) {
+        if (smem_u32(smem) & 1023u) {
+            printf("b2 attn: dynamic smem base not 1024-aligned\n");
+            __trap();
+        }
+        tma_prefetch_desc(&p.tmq);
+        tma_prefetch_desc(&p.tmk);
+        tma_prefetch_desc(&p.tmv);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < AT_STAGES; ++s) {
+            mbar_init(&kv_full[s], 1);
+            mbar_init(&kv_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&s_empty[s], 128);
+        }
+        mbar_init(p_full, 128);
+        mbar_init(o_done, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, AT_TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            mbar_expect_tx(q_full, Q_BYTES);
+#pragma unroll
+            for (int a = 0; a < DA; ++a)
+                tma_load_2d(sQ + a * (AT_BQ * 128), &p.tmq, q_full, h * DP + a * 64, b * p.sq + q0);
+            for (int j = 0; j < nblk; ++j) {
+                const int st = j % AT_STAGES;
+                mbar_wait(&kv_empty[st], ((j / AT_STAGES) & 1) ^ 1);
+                uint8_t* sk = sKV + st * STAGE_BYTES;
+                uint8_t* sv = sk + K_BYTES;
+                mbar_expect_tx(&kv_full[st], STAGE_BYTES);
+#pragma unroll
+                for (int a = 0; a < DA; ++a)
+                    tma_load_2d(sk + a * (BKV * 128), &p.tmk, &kv_full[st], h * DP + a * 64,
+                                (int)(b * p.k_bstride) + j * BKV);
+#pragma unroll
+                for (int a = 0; a < KVA; ++a)
+                    tma_load_2d(sv + a * (DP * 128), &p.tmv, &kv_full[st],
+                                (int)(b * p.vt_bstride) + j * BKV + a * 64, h * DP);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            const uint32_t idesc_s = make_idesc_f16(AT_BQ, BKV);
+            const uint32_t idesc_o = make_idesc_f16(AT_BQ, DP);
+            auto issue_qk = [&](int j) {
+                const int st = j % AT_STAGES;
+                mbar_wait(&kv_full[st], (j / AT_STAGES) & 1);
+                mbar_wait(&s_empty[j & 1], ((j >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t sk = smem_u32(sKV + st * STAGE_BYTES);
+                const uint32_t tS = tmem_base + ((j & 1) ? AT_TMEM_S1 : AT_TMEM_S0);
+#pragma unroll
+                for (int a = 0; a < DA; ++a) {
+                    const uint64_t dq = make_kmajor_sw128_desc(smem_u32(sQ) + a * (AT_BQ * 128));
+                    const uint64_t dk = make_kmajor_sw128_desc(sk + a * (BKV * 128));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_f16(tS, dq + 2 * k, dk + 2 * k, idesc_s, (a | k) ? 1u : 0u);
+                }
+                umma_commit(&s_full[j & 1]);
+            };
+            mbar_wait(q_full, 0);
+            issue_qk(0);
+            for (int j = 0; j < nblk; ++j) {
+                if (j + 1 < nblk) issue_qk(j + 1);  // overlaps softmax(j)
+                const int st = j % AT_STAGES;
+                mbar_wait(p_full, j & 1);
+                tc_fence_after();
+                const uint32_t sv = smem_u32(sKV + st * STAGE_BYTES + K_BYTES);
+#pragma unroll
+                for (int a = 0; a < KVA; ++a) {
+                    const uint64_t dp = make_kmajor_sw128_desc(smem_u32(sP) + a * (AT_BQ * 128));
+                    const uint64_t dv = make_kmajor_sw128_desc(sv + a * (DP * 128));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_f16(tmem_base + AT_TMEM_O, dp + 2 * k, dv + 2 * k, idesc_o,
+                                 (j > 0 || a > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(o_done);
+                umma_commit(&kv_empty[st]);
+            }
+        }
+    } else {
+        // ===== softmax / correction / epilogue: thread owns query row r =====
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int j = 0; j < nblk; ++j) {
+            const uint32_t tS = lane_addr + ((j & 1) ? AT_TMEM_S1 : AT_TMEM_S0);
+            const int kv_valid = p.skv - j * BKV;  // columns >= kv_valid are masked
+            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+            tc_fence_after();
+            // pass 1: row max
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < BKV; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(tS + c, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (c + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+            }
+            const float m_new = fmaxf(m_run, mx * p.scale_log2);
+            const float alpha = ex2_approx(m_run - m_new);
+            if (j > 0) mbar_wait(o_done, (j - 1) & 1);  // PV(j-1) retired: P buffer + O are ours
+            // pass 2: P = exp2(s*scale - m), to smem (fp16, swizzled K-major), row sum
+            float rs = 0.f;
+#pragma unroll
+            for (int c = 0; c < BKV; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(tS + c, v);
+                tmem_ld_wait();
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float p0 = (c + i < kv_valid) ? ex2_approx(__uint_as_float(v[i]) * p.scale_log2 - m_new) : 0.f;
+                    float p1 = (c + i + 1 < kv_valid) ? ex2_approx(__uint_as_float(v[i + 1]) * p.scale_log2 - m_new) : 0.f;
+                    __half2 hp = __floats2half2_rn(p0, p1);
+                    const float2 back = __half22float2(hp);
+                    rs += back.x + back.y;  // normaliser sums exactly what the MMA consumes
+                    pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hp);
+                }
+                const int atom = c >> 6;
+                uint8_t* prow = sP + atom * (AT_BQ * 128);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t chunk = ((c & 63) >> 3) + u;
+                    *reinterpret_cast<uint4*>(prow + sw128_offset(r, chunk)) =
+                        make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+                }
+            }
+            // S(j) fully consumed
+            tc_fence_before();
+            mbar_arrive(&s_empty[j & 1]);
+            // rescale the running O accumulator (TMEM) when any row of this warp moved its max
+            if (j > 0) {
+                const bool need = __any_sync(0xffffffffu, alpha != 1.0f);
+                if (need) {
+#pragma unroll
+                    for (int c = 0; c < DP; c += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(lane_addr + AT_TMEM_O + c, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                        tmem_st32(lane_addr + AT_TMEM_O + c, v);
+                    }
+                    tmem_st_wait();
+                }
+            }
+            l_run = l_run * alpha + rs;
+            m_run = m_new;
+            fence_proxy_async_smem();  // P stores -> visible to the UMMA (async proxy)
+            tc_fence_before();
+            mbar_arrive(p_full);
+        }
+        // epilogue: O / l -> fp16 -> global
+        mbar_wait(o_done, (nblk - 1) & 1);
+        tc_fence_after();
+        const float inv_l = 1.0f / l_run;
+        const bool row_ok = (q0 + r) < p.sq;
+        __half* orow = p.out + ((long)b * p.sq + q0 + r) * p.ldo + h * p.d_real;
+#pragma unroll
+        for (int c = 0; c < DP; c += 32) {
+            uint32_t v[32];
+            tmem_ld32(lane_addr + AT_TMEM_O + c, v);
+            tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int col = c + 8 * u;
+                    if (col + 8 <= p.d_real) {
+                        uint4 o;
+                        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            oh[i] = __floats2half2_rn(__uint_as_float(v[8 * u + 2 * i]) * inv_l,
+                                                      __uint_as_float(v[8 * u + 2 * i + 1]) * inv_l);
+                        *reinterpret_cast<uint4*>(orow + col) = o;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, AT_TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------ host
+static int encode_2d(CUtensorMap* m, const __half* ptr, long cols, long rows, long ld, int box_cols, int box_rows,
+                     const char* what) {
+    static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
+    if (!enc) {
+        void* fp = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres);
+        if (err != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fp) {
+            b2_set_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed");
+            return -1;
+        }
+        enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fp);
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        b2_set_error("attn: cuTensorMapEncodeTiled(%s) failed: %d (cols %ld rows %ld ld %ld box %d,%d)", what, (int)r,
+                     cols, rows, ld, box_cols, box_rows);
+        return -1;
+    }
+    return 0;
+}
+
+static size_t attn_smem_bytes(int da, int bkv) {
+    const size_t q = (size_t)da * AT_BQ * 128;
+    const size_t k = (size_t)da * bkv * 128;
+    const size_t v = (size_t)(bkv / 64) * da * 64 * 128;
+    const size_t pb = (size_t)(bkv / 64) * AT_BQ * 128;
+    return q + AT_STAGES * (k + v) + pb + 256;
+}
+
+int attn_plan(const AttnDesc& d, AttnPlan* plan) {
+    memset(plan, 0, sizeof(*plan));
+    if (d.dp != 64 && d.dp != 128 && d.dp != 192) {
+        b2_set_error("attn: padded head dim %d unsupported", d.dp);
+        return -1;
+    }
+    if (d.d_real > d.dp || (d.d_real & 7) || (d.ldo & 7) || (d.ldq & 7) || (d.ldk & 7) || (d.ldvt & 7)) {
+        b2_set_error("attn: bad dims d_real %d dp %d", d.d_real, d.dp);
+        return -1;
+    }
+    plan->d = d;
+    const int bkv = (d.dp == 192) ? 64 : 128;
+    if (encode_2d(&plan->tmq, d.q, (long)d.heads * d.dp, (long)d.nb * d.sq, d.ldq, 64, AT_BQ, "q")) return -1;
+    if (encode_2d(&plan->tmk, d.k, (long)d.heads * d.dp, d.k_rows, d.ldk, 64, bkv, "k")) return -1;
+    if (encode_2d(&plan->tmv, d.vt, d.vt_cols, (long)d.heads * d.dp, d.ldvt, 64, d.dp, "vt")) return -1;
+    plan->grid = dim3((d.sq + AT_BQ - 1) / AT_BQ, d.heads, d.nb);
+    plan->smem = attn_smem_bytes(d.dp / 64, bkv);
+    return 0;
+}
+
+int attn_launch(const AttnPlan& plan, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(attn_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(attn_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_set = true;
+    }
+    const AttnDesc& d = plan.d;
+    AttnParams p;
+    p.tmq = plan.tmq; p.tmk = plan.tmk; p.tmv = plan.tmv;
+    p.out = d.out; p.ldo = d.ldo;
+    p.sq = d.sq; p.skv = d.skv; p.heads = d.heads; p.d_real = d.d_real;
+    p.k_bstride = d.k_bstride; p.vt_bstride = d.vt_bstride;
+    p.scale_log2 = (float)(1.4426950408889634 / sqrt((double)d.d_real));
+    if (d.dp == 64) attn_kernel<1, 128><<<plan.grid, AT_THREADS, plan.smem, s>>>(p);
+    else if (d.dp == 128) attn_kernel<2, 128><<<plan.grid, AT_THREADS, plan.smem, s>>>(p);
+    else attn_kernel<3, 64><<<plan.grid, AT_THREADS, plan.smem, s>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        b2_set_error("attn launch: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    return 0;
+}
+
+}  // namespace b2

@@ -1,6 +1,8 @@
 // extern "C" surface of libb200sd.so (declared in include/b200sd.h).
 #include "../../include/b200sd.h"
 
+#include "attention.cuh"
+#include "elementwise.cuh"
 #include "igemm.cuh"
 
 using namespace b2;
@@ -53,6 +55,62 @@ int b2sd_op_igemm(const b2sd_igemm_desc* d, void* stream) {
 
 uint64_t b2sd_igemm_partial_floats(int splits, int64_t rows_total, int n_valid) {
     return igemm_partial_floats(splits, rows_total, n_valid);
+}
+
+int b2sd_op_attention(const b2sd_attn_desc* d, void* stream) {
+    AttnDesc a{};
+    a.q = reinterpret_cast<const __half*>(d->q); a.ldq = d->ldq;
+    a.k = reinterpret_cast<const __half*>(d->k); a.ldk = d->ldk; a.k_bstride = d->k_bstride; a.k_rows = d->k_rows;
+    a.vt = reinterpret_cast<const __half*>(d->vt); a.ldvt = d->ldvt; a.vt_bstride = d->vt_bstride; a.vt_cols = d->vt_cols;
+    a.out = reinterpret_cast<__half*>(d->out); a.ldo = d->ldo;
+    a.nb = d->nb; a.heads = d->heads; a.sq = d->sq; a.skv = d->skv; a.d_real = d->d_real; a.dp = d->dp;
+    AttnPlan plan;
+    if (attn_plan(a, &plan)) return -1;
+    return attn_launch(plan, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b2sd_op_groupnorm(const void* xa, int ca, int lda, const void* xb, int cb, int ldb, const float* gamma,
+                      const float* beta, void* y, int ldy, int nb, int hw, int groups, float eps, int silu,
+                      void* stream) {
+    GroupNormArgs a{};
+    a.xa = reinterpret_cast<const __half*>(xa); a.ca = ca; a.lda = lda;
+    a.xb = reinterpret_cast<const __half*>(xb); a.cb = cb; a.ldb = ldb;
+    a.gamma = gamma; a.beta = beta;
+    a.y = reinterpret_cast<__half*>(y); a.ldy = ldy;
+    a.nb = nb; a.hw = hw; a.groups = groups; a.eps = eps; a.silu = silu;
+    return groupnorm_launch(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b2sd_op_layernorm(const void* x, int ldx, const float* gamma, const float* beta, void* y, int ldy,
+                      int64_t rows, int c, float eps, void* stream) {
+    return layernorm_launch(reinterpret_cast<const __half*>(x), ldx, gamma, beta, reinterpret_cast<__half*>(y), ldy,
+                            rows, c, eps, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b2sd_op_upsample2x(const void* x, void* y, int nb, int h, int w, int c, void* stream) {
+    return upsample2x_launch(reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), nb, h, w, c,
+                             reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b2sd_op_smallconv(const void* x, const void* w_oihw, const float* bias, void* y, int ldy, int nb, int h,
+                      int w, int cin, int cout, int in_h, int in_w, int flags, void* stream) {
+    SmallConvArgs a{};
+    a.x = x; a.w = reinterpret_cast<const __half*>(w_oihw); a.bias = bias;
+    a.y = reinterpret_cast<__half*>(y); a.ldy = ldy;
+    a.nb = nb; a.h = h; a.w_ = w; a.cin = cin; a.cout = cout; a.in_h = in_h; a.in_w = in_w; a.flags = flags;
+    return smallconv_launch(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b2sd_op_lcm_step(void* x, const void* eps, const void* noise, const float* coef, void* out_latent, int T,
+                     int hw, int do_add_noise, void* stream) {
+    return lcm_step_launch(reinterpret_cast<__half*>(x), reinterpret_cast<const __half*>(eps),
+                           reinterpret_cast<const __half*>(noise), coef, reinterpret_cast<__half*>(out_latent), T, hw,
+                           do_add_noise, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b2sd_op_post_u8(const void* y_nhwc, int ldy, void* out_nchw_u8, int nb, int h, int w, void* stream) {
+    return post_u8_launch(reinterpret_cast<const __half*>(y_nhwc), ldy, reinterpret_cast<uint8_t*>(out_nchw_u8), nb,
+                          h, w, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,466 @@
+// SIMT helper kernels: normalisation, resampling, tiny convolutions, scheduler step, pre/post.
+#include "elementwise.cuh"
+
+#include "igemm.cuh"  // b2_set_error
+
+namespace b2 {
+
+#define B2_CHECK_LAUNCH(name)                                              \
+    do {                                                                   \
+        cudaError_t e__ = cudaGetLastError();                              \
+        if (e__ != cudaSuccess) {                                          \
+            b2_set_error("%s launch: %s", name, cudaGetErrorString(e__));  \
+            return -1;                                                     \
+        }                                                                  \
+    } while (0)
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+template <typename T>
+__device__ __forceinline__ T block_reduce_sum(T v, T* scratch) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    T r = (threadIdx.x < nw) ? scratch[threadIdx.x] : T(0);
+    if (warp == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        if (lane == 0) scratch[0] = r;
+    }
+    __syncthreads();
+    return scratch[0];
+}
+
+// ------------------------------------------------------------------------------------------ GroupNorm
+// one CTA per (group, batch item); two passes over an L2-resident slab (stats, then normalise+SiLU)
+__global__ void __launch_bounds__(512) groupnorm_kernel(GroupNormArgs a) {
+    __shared__ float scratch[32];
+    const int g = blockIdx.x, b = blockIdx.y;
+    const int C = a.ca + a.cb;
+    const int cpg = C / a.groups;
+    const int hp = cpg >> 1;  // half2 per pixel in this group
+    const long total = (long)a.hw * hp;
+    const int cbase = g * cpg;
+    float s = 0.f, ss = 0.f;
+    for (long e = threadIdx.x; e < total; e += blockDim.x) {
+        const int p = (int)(e / hp);
+        const int c = cbase + 2 * (int)(e % hp);
+        const __half2 v = (c < a.ca)
+                              ? *reinterpret_cast<const __half2*>(a.xa + ((long)b * a.hw + p) * a.lda + c)
+                              : *reinterpret_cast<const __half2*>(a.xb + ((long)b * a.hw + p) * a.ldb + (c - a.ca));
+        const float2 f = __half22float2(v);
+        s += f.x + f.y;
+        ss += f.x * f.x + f.y * f.y;
+    }
+    s = block_reduce_sum(s, scratch);
+    ss = block_reduce_sum(ss, scratch);
+    const float inv_n = 1.0f / (float)(a.hw * (long)cpg);
+    const float mean = s * inv_n;
+    const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + a.eps);
+    for (long e = threadIdx.x; e < total; e += blockDim.x) {
+        const int p = (int)(e / hp);
+        const int c = cbase + 2 * (int)(e % hp);
+        const __half2 v = (c < a.ca)
+                              ? *reinterpret_cast<const __half2*>(a.xa + ((long)b * a.hw + p) * a.lda + c)
+                              : *reinterpret_cast<const __half2*>(a.xb + ((long)b * a.hw + p) * a.ldb + (c - a.ca));
+        const float2 f = __half22float2(v);
+        float y0 = (f.x - mean) * rstd * a.gamma[c] + a.beta[c];
+        float y1 = (f.y - mean) * rstd * a.gamma[c + 1] + a.beta[c + 1];
+        if (a.silu) {
+            y0 = silu_f(y0);
+            y1 = silu_f(y1);
+        }
+        *reinterpret_cast<__half2*>(a.y + ((long)b * a.hw + p) * a.ldy + c) = __floats2half2_rn(y0, y1);
+    }
+}
+
+int groupnorm_launch(const GroupNormArgs& a, cudaStream_t s) {
+    const int C = a.ca + a.cb;
+    if (C % a.groups != 0 || ((C / a.groups) & 1) || (a.ca & 1) || (a.lda & 1) || (a.cb && (a.ldb & 1)) || (a.ldy & 1)) {
+        b2_set_error("groupnorm: unsupported channels %d+%d groups %d", a.ca, a.cb, a.groups);
+        return -1;
+    }
+    groupnorm_kernel<<<dim3(a.groups, a.nb), 512, 0, s>>>(a);
+    B2_CHECK_LAUNCH("groupnorm");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ LayerNorm
+__global__ void layernorm_kernel(const __half* __restrict__ x, int ldx, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, __half* __restrict__ y, int ldy, long rows,
+                                 int c, float eps) {
+    const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const __half* xr = x + row * ldx;
+    const int chunks = c >> 3;
+    float s = 0.f, ss = 0.f;
+    for (int k = lane; k < chunks; k += 32) {
+        const uint4 u = reinterpret_cast<const uint4*>(xr)[k];
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(h[i]);
+            s += f.x + f.y;
+            ss += f.x * f.x + f.y * f.y;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    const float mean = s / c;
+    const float rstd = rsqrtf(fmaxf(ss / c - mean * mean, 0.f) + eps);
+    __half* yr = y + row * ldy;
+    for (int k = lane; k < chunks; k += 32) {
+        const uint4 u = reinterpret_cast<const uint4*>(xr)[k];
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(h[i]);
+            const int cc = k * 8 + 2 * i;
+            oh[i] = __floats2half2_rn((f.x - mean) * rstd * gamma[cc] + beta[cc],
+                                      (f.y - mean) * rstd * gamma[cc + 1] + beta[cc + 1]);
+        }
+        reinterpret_cast<uint4*>(yr)[k] = o;
+    }
+}
+
+int layernorm_launch(const __half* x, int ldx, const float* gamma, const float* beta, __half* y, int ldy,
+                     long rows, int c, float eps, cudaStream_t s) {
+    if ((c & 7) || (ldx & 7) || (ldy & 7)) {
+        b2_set_error("layernorm: c/ld must be multiples of 8 (c=%d)", c);
+        return -1;
+    }
+    const int wpb = 8;
+    layernorm_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, s>>>(x, ldx, gamma, beta, y, ldy, rows, c, eps);
+    B2_CHECK_LAUNCH("layernorm");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ upsample
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int nb, int h, int w, int c8) {
+    const long total = (long)nb * (2 * h) * (2 * w) * c8;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const int cc = (int)(e % c8);
+        long p = e / c8;
+        const int wo = (int)(p % (2 * w));
+        p /= (2 * w);
+        const int ho = (int)(p % (2 * h));
+        const int n = (int)(p / (2 * h));
+        y[e] = x[(((long)n * h + (ho >> 1)) * w + (wo >> 1)) * c8 + cc];
+    }
+}
+
+int upsample2x_launch(const __half* x, __half* y, int nb, int h, int w, int c, cudaStream_t s) {
+    if (c & 7) {
+        b2_set_error("upsample2x: c %% 8 != 0");
+        return -1;
+    }
+    const long total = (long)nb * 4 * h * w * (c / 8);
+    const int threads = 256;
+    long blocks = (total + threads - 1) / threads;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    upsample2x_kernel<<<(unsigned)blocks, threads, 0, s>>>(reinterpret_cast<const uint4*>(x),
+                                                           reinterpret_cast<uint4*>(y), nb, h, w, c / 8);
+    B2_CHECK_LAUNCH("upsample2x");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ small conv
+// thread = (pixel, 8 output channels); weights staged in smem as fp32 [k][cout]
+template <int CIN>
+__global__ void __launch_bounds__(256) smallconv_kernel(SmallConvArgs a) {
+    extern __shared__ float ws[];  // [CIN*9][cout] then bias[cout]
+    constexpr int K = CIN * 9;
+    const int cout = a.cout;
+    for (int i = threadIdx.x; i < K * cout; i += blockDim.x) {
+        const int o = i % cout, k = i / cout;  // k = tap*CIN + c
+        const int tap = k / CIN, c = k % CIN;
+        ws[i] = __half2float(a.w[((long)o * CIN + c) * 9 + tap]);
+    }
+    float* bs = ws + K * cout;
+    for (int i = threadIdx.x; i < cout; i += blockDim.x) bs[i] = a.bias ? a.bias[i] : 0.f;
+    __syncthreads();
+    const int groups = cout >> 3;
+    const long total = (long)a.nb * a.h * a.w_ * groups;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(e % groups);
+        long p = e / groups;
+        const int xw = (int)(p % a.w_);
+        const int yh = (int)((p / a.w_) % a.h);
+        const int n = (int)(p / ((long)a.w_ * a.h));
+        float patch[K];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int yy = yh + tap / 3 - 1, xx = xw + tap % 3 - 1;
+            const bool in = (yy >= 0) && (yy < a.h) && (xx >= 0) && (xx < a.w_);
+            // nearest resize (VaeImageProcessor.resize -> F.interpolate default mode): src = floor(dst*in/out)
+            const int sy = in ? (int)(((long)yy * a.in_h) / a.h) : 0;
+            const int sx = in ? (int)(((long)xx * a.in_w) / a.w_) : 0;
+            const long base = (((long)n * a.in_h + sy) * a.in_w + sx) * CIN;
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) {
+                float v = 0.f;
+                if (in) {
+                    if (a.flags & SC_IN_U8) {
+                        // lib/pipeline.py:61 convertto(scale=1/255); the 2x-1 of VaeImageProcessor and the
+                        // (x+1)/2 of EncoderTiny cancel
+                        v = (float)reinterpret_cast<const uint8_t*>(a.x)[base + c] * (1.0f / 255.0f);
+                    } else {
+                        v = __half2float(reinterpret_cast<const __half*>(a.x)[base + c]);
+                        if (a.flags & SC_IN_TANH3) v = tanhf(v * (1.0f / 3.0f)) * 3.0f;
+                    }
+                    // operands of the reference engines are fp16
+                    v = __half2float(__float2half_rn(v));
+                }
+                patch[tap * CIN + c] = v;
+            }
+        }
+        float acc[8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) acc[o] = bs[cg * 8 + o];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float4 w0 = *reinterpret_cast<const float4*>(&ws[k * cout + cg * 8]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&ws[k * cout + cg * 8 + 4]);
+            const float v = patch[k];
+            acc[0] += v * w0.x; acc[1] += v * w0.y; acc[2] += v * w0.z; acc[3] += v * w0.w;
+            acc[4] += v * w1.x; acc[5] += v * w1.y; acc[6] += v * w1.z; acc[7] += v * w1.w;
+        }
+        uint4 u;
+        __half2* hh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            float v0 = acc[2 * o], v1 = acc[2 * o + 1];
+            if (a.flags & SC_OUT_RELU) {
+                v0 = fmaxf(v0, 0.f);
+                v1 = fmaxf(v1, 0.f);
+            }
+            hh[o] = __floats2half2_rn(v0, v1);
+        }
+        *reinterpret_cast<uint4*>(a.y + p * a.ldy + cg * 8) = u;
+    }
+}
+
+int smallconv_launch(const SmallConvArgs& a, cudaStream_t s) {
+    if ((a.cout & 7) || (a.ldy & 7) || (a.cin != 3 && a.cin != 4)) {
+        b2_set_error("smallconv: cin %d cout %d unsupported", a.cin, a.cout);
+        return -1;
+    }
+    const size_t smem = ((size_t)a.cin * 9 * a.cout + a.cout) * sizeof(float);
+    const long total = (long)a.nb * a.h * a.w_ * (a.cout / 8);
+    long blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (a.cin == 3) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(smallconv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        smallconv_kernel<3><<<(unsigned)blocks, 256, smem, s>>>(a);
+    } else {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(smallconv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        smallconv_kernel<4><<<(unsigned)blocks, 256, smem, s>>>(a);
+    }
+    B2_CHECK_LAUNCH("smallconv");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ LCM step
+__global__ void lcm_step_kernel(__half* __restrict__ x, const __half* __restrict__ eps,
+                                const __half* __restrict__ noise, const float* __restrict__ coef,
+                                __half* __restrict__ out_latent, int T, int hw, int do_add_noise) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= hw) return;
+    const float* alpha = coef;
+    const float* beta = coef + T;
+    const float* c_skip = coef + 2 * T;
+    const float* c_out = coef + 3 * T;
+    float prev[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < T; ++i) {
+        const long off = ((long)i * hw + p) * 4;
+        const uint2 ux = *reinterpret_cast<const uint2*>(x + off);
+        const uint2 ue = *reinterpret_cast<const uint2*>(eps + off);
+        const __half2* hx = reinterpret_cast<const __half2*>(&ux);
+        const __half2* he = reinterpret_cast<const __half2*>(&ue);
+        float xv[4], ev[4], x0[4];
+        *reinterpret_cast<float2*>(&xv[0]) = __half22float2(hx[0]);
+        *reinterpret_cast<float2*>(&xv[2]) = __half22float2(hx[1]);
+        *reinterpret_cast<float2*>(&ev[0]) = __half22float2(he[0]);
+        *reinterpret_cast<float2*>(&ev[2]) = __half22float2(he[1]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float f = (xv[c] - beta[i] * ev[c]) / alpha[i];
+            x0[c] = c_out[i] * f + c_skip[i] * xv[c];
+        }
+        if (i > 0) {
+            // slot i of the next call = re-noised x0 of slot i-1 (computed last iteration)
+            float nv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (do_add_noise) {
+                const uint2 un = *reinterpret_cast<const uint2*>(noise + off);
+                const __half2* hn = reinterpret_cast<const __half2*>(&un);
+                *reinterpret_cast<float2*>(&nv[0]) = __half22float2(hn[0]);
+                *reinterpret_cast<float2*>(&nv[2]) = __half22float2(hn[1]);
+            }
+            uint2 uo;
+            __half2* ho = reinterpret_cast<__half2*>(&uo);
+            ho[0] = __floats2half2_rn(alpha[i] * prev[0] + beta[i] * nv[0], alpha[i] * prev[1] + beta[i] * nv[1]);
+            ho[1] = __floats2half2_rn(alpha[i] * prev[2] + beta[i] * nv[2], alpha[i] * prev[3] + beta[i] * nv[3]);
+            *reinterpret_cast<uint2*>(x + off) = uo;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) prev[c] = x0[c];
+    }
+    uint2 uo;
+    __half2* ho = reinterpret_cast<__half2*>(&uo);
+    ho[0] = __floats2half2_rn(prev[0], prev[1]);
+    ho[1] = __floats2half2_rn(prev[2], prev[3]);
+    *reinterpret_cast<uint2*>(out_latent + (long)p * 4) = uo;
+}
+
+int lcm_step_launch(__half* x, const __half* eps, const __half* noise, const float* coef, __half* out_latent,
+                    int T, int hw, int do_add_noise, cudaStream_t s) {
+    lcm_step_kernel<<<(hw + 127) / 128, 128, 0, s>>>(x, eps, noise, coef, out_latent, T, hw, do_add_noise);
+    B2_CHECK_LAUNCH("lcm_step");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ post
+__global__ void post_u8_kernel(const __half* __restrict__ y, int ldy, uint8_t* __restrict__ out, int nb, int h, int w) {
+    const long hw = (long)h * w;
+    const long total = (long)nb * hw;
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    const int n = (int)(p / hw);
+    const long q = p % hw;
+    const __half one = __float2half(1.0f), half_ = __float2half(0.5f), two = __float2half(2.0f);
+    const __half zero = __float2half(0.0f), s255 = __float2half(255.0f);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        __half v = y[p * ldy + c];
+        v = __hsub(__hmul(v, two), one);        // DecoderTiny.forward: x.mul(2).sub(1)
+        v = __hadd(__hmul(v, half_), half_);    // postprocess_image: x / 2 + 0.5
+        v = __hmax(zero, __hmin(v, one));       // .clamp(0, 1)
+        v = __hmul(v, s255);                    // lib/pipeline.py:74  frame * 255.0
+        v = __hmax(zero, __hmin(v, s255));      // .clamp(0, 255)
+        out[((long)n * 3 + c) * hw + q] = (uint8_t)__half2int_rz(v);  // .to(uint8): truncation
+    }
+}
+
+int post_u8_launch(const __half* y_nhwc, int ldy, uint8_t* out_nchw, int nb, int h, int w, cudaStream_t s) {
+    const long total = (long)nb * h * w;
+    post_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(y_nhwc, ldy, out_nchw, nb, h, w);
+    B2_CHECK_LAUNCH("post_u8");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ prepare-time
+__global__ void small_linear_kernel(const float* __restrict__ in, int in_ld, const __half* __restrict__ w,
+                                    const float* __restrict__ bias, float* __restrict__ out, int out_ld, int nb,
+                                    int n, int k, int silu_in) {
+    const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= (long)nb * n) return;
+    const int b = (int)(warp / n), j = (int)(warp % n);
+    float acc = 0.f;
+    for (int i = lane; i < k; i += 32) {
+        float v = in[(long)b * in_ld + i];
+        if (silu_in) v = v / (1.0f + expf(-v));
+        acc += v * __half2float(w[(long)j * k + i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[(long)b * out_ld + j] = acc + (bias ? bias[j] : 0.f);
+}
+
+int small_linear_launch(const float* in, int in_ld, const __half* w, const float* bias, float* out, int out_ld,
+                        int nb, int n, int k, int silu_in, cudaStream_t s) {
+    const long warps = (long)nb * n;
+    small_linear_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(in, in_ld, w, bias, out, out_ld, nb, n, k, silu_in);
+    B2_CHECK_LAUNCH("small_linear");
+    return 0;
+}
+
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out, int nb, int dim) {
+    const int half_dim = dim / 2;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb * half_dim) return;
+    const int b = i / half_dim, j = i % half_dim;
+    const float freq = expf(-logf(10000.0f) * (float)j / (float)half_dim);
+    const float arg = t[b] * freq;
+    out[(long)b * dim + j] = cosf(arg);             // flip_sin_to_cos=True: [cos | sin]
+    out[(long)b * dim + half_dim + j] = sinf(arg);
+}
+
+int timestep_embedding_launch(const float* t, float* out, int nb, int dim, cudaStream_t s) {
+    const int total = nb * (dim / 2);
+    timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, s>>>(t, out, nb, dim);
+    B2_CHECK_LAUNCH("timestep_embedding");
+    return 0;
+}
+
+__global__ void cast_f32_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, long n) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        y[i] = __float2half_rn(x[i]);
+}
+__global__ void cast_f16_f32_kernel(const __half* __restrict__ x, float* __restrict__ y, long n) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        y[i] = __half2float(x[i]);
+}
+static unsigned grid_for(long n) {
+    long b = (n + 255) / 256;
+    if (b > 148 * 32) b = 148 * 32;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+int cast_f32_to_f16_launch(const float* x, __half* y, long n, cudaStream_t s) {
+    cast_f32_f16_kernel<<<grid_for(n), 256, 0, s>>>(x, y, n);
+    B2_CHECK_LAUNCH("cast_f32_f16");
+    return 0;
+}
+int cast_f16_to_f32_launch(const __half* x, float* y, long n, cudaStream_t s) {
+    cast_f16_f32_kernel<<<grid_for(n), 256, 0, s>>>(x, y, n);
+    B2_CHECK_LAUNCH("cast_f16_f32");
+    return 0;
+}
+
+__global__ void pack_conv_weight_kernel(const __half* __restrict__ w, __half* __restrict__ dst, int dst_ld, int koff,
+                                        int o, int i, int taps, int c0, int cn) {
+    const long total = (long)o * taps * cn;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(e % cn);
+        const int tap = (int)((e / cn) % taps);
+        const int oo = (int)(e / ((long)cn * taps));
+        dst[(long)oo * dst_ld + koff + tap * cn + c] = w[((long)oo * i + (c0 + c)) * taps + tap];
+    }
+}
+int pack_conv_weight_launch(const __half* w_oihw, __half* dst, int dst_ld, int koff, int o, int i, int taps, int c0,
+                            int cn, cudaStream_t s) {
+    pack_conv_weight_kernel<<<grid_for((long)o * taps * cn), 256, 0, s>>>(w_oihw, dst, dst_ld, koff, o, i, taps, c0, cn);
+    B2_CHECK_LAUNCH("pack_conv_weight");
+    return 0;
+}
+
+__global__ void gather_rows_kernel(const __half* __restrict__ src, int src_ld, const int* __restrict__ perm,
+                                   __half* __restrict__ dst, int dst_ld, int rows, int cols) {
+    const long total = (long)rows * cols;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(e % cols);
+        const int r = (int)(e / cols);
+        const int sr = perm ? perm[r] : r;
+        dst[(long)r * dst_ld + c] = sr >= 0 ? src[(long)sr * src_ld + c] : __float2half(0.f);
+    }
+}
+int gather_rows_launch(const __half* src, int src_ld, const int* perm, __half* dst, int dst_ld, int rows, int cols,
+                       cudaStream_t s) {
+    gather_rows_kernel<<<grid_for((long)rows * cols), 256, 0, s>>>(src, src_ld, perm, dst, dst_ld, rows, cols);
+    B2_CHECK_LAUNCH("gather_rows");
+    return 0;
+}
+
+}  // namespace b2

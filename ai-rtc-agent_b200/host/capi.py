@@ -32,6 +32,17 @@ class IgemmDesc(C.Structure):
     ]
 
 
+class AttnDesc(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("ldq", C.c_int),
+        ("k", C.c_void_p), ("ldk", C.c_int), ("k_bstride", C.c_int64), ("k_rows", C.c_int64),
+        ("vt", C.c_void_p), ("ldvt", C.c_int), ("vt_bstride", C.c_int64), ("vt_cols", C.c_int64),
+        ("out", C.c_void_p), ("ldo", C.c_int),
+        ("nb", C.c_int), ("heads", C.c_int), ("sq", C.c_int), ("skv", C.c_int), ("d_real", C.c_int),
+        ("dp", C.c_int),
+    ]
+
+
 IG_RELU = 1
 IG_GEGLU = 2
 
@@ -52,6 +63,16 @@ def lib() -> C.CDLL:
         _lib.b2sd_op_igemm.restype = C.c_int
         _lib.b2sd_igemm_partial_floats.argtypes = [C.c_int, C.c_int64, C.c_int]
         _lib.b2sd_igemm_partial_floats.restype = C.c_uint64
+        vp, ci, cf, i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
+        _lib.b2sd_op_attention.argtypes = [C.POINTER(AttnDesc), vp]
+        _lib.b2sd_op_groupnorm.argtypes = [vp, ci, ci, vp, ci, ci, vp, vp, vp, ci, ci, ci, ci, cf, ci, vp]
+        _lib.b2sd_op_layernorm.argtypes = [vp, ci, vp, vp, vp, ci, i64, ci, cf, vp]
+        _lib.b2sd_op_upsample2x.argtypes = [vp, vp, ci, ci, ci, ci, vp]
+        _lib.b2sd_op_smallconv.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
+        _lib.b2sd_op_lcm_step.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, vp]
+        _lib.b2sd_op_post_u8.argtypes = [vp, ci, vp, ci, ci, ci, vp]
+        for name in ("attention", "groupnorm", "layernorm", "upsample2x", "smallconv", "lcm_step", "post_u8"):
+            getattr(_lib, "b2sd_op_" + name).restype = C.c_int
     return _lib
 
 

@@ -63,3 +63,66 @@ def igemm(srcs: Sequence[Tuple[torch.Tensor, int]], w: torch.Tensor, out: torch.
     if keep:
         torch.cuda.current_stream().synchronize()
     return out
+
+
+def _sp():
+    return capi.current_stream_ptr()
+
+
+def attention(q, k, vt, out, *, nb, heads, sq, skv, d_real, dp, k_bstride, vt_bstride):
+    """q [nb*sq, >=heads*dp], k [rows, >=heads*dp], vt [heads*dp, cols] (2-D fp16 views), out [nb*sq, heads*d_real]."""
+    d = capi.AttnDesc()
+    d.q, d.ldq = q.data_ptr(), q.stride(0)
+    d.k, d.ldk, d.k_bstride, d.k_rows = k.data_ptr(), k.stride(0), k_bstride, k.shape[0]
+    d.vt, d.ldvt, d.vt_bstride, d.vt_cols = vt.data_ptr(), vt.stride(0), vt_bstride, vt.shape[1]
+    d.out, d.ldo = out.data_ptr(), out.stride(0)
+    d.nb, d.heads, d.sq, d.skv, d.d_real, d.dp = nb, heads, sq, skv, d_real, dp
+    capi.check(capi.lib().b2sd_op_attention(C.byref(d), _sp()), "b2sd_op_attention")
+    return out
+
+
+def groupnorm(xa, xb, gamma, beta, y, *, groups=32, eps=1e-5, silu=True):
+    """xa/xb: NHWC fp16 (xb may be None); y: NHWC fp16 with C = ca + cb."""
+    nb, h, w, ca = xa.shape
+    cb = 0 if xb is None else xb.shape[3]
+    capi.check(capi.lib().b2sd_op_groupnorm(
+        xa.data_ptr(), ca, xa.stride(2), 0 if xb is None else xb.data_ptr(), cb, 0 if xb is None else xb.stride(2),
+        gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), y.stride(2), nb, h * w, groups, eps, int(silu), _sp()),
+        "b2sd_op_groupnorm")
+    return y
+
+
+def layernorm(x, gamma, beta, y, eps=1e-5):
+    rows, c = x.shape
+    capi.check(capi.lib().b2sd_op_layernorm(x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(),
+                                            y.data_ptr(), y.stride(0), rows, c, eps, _sp()), "b2sd_op_layernorm")
+    return y
+
+
+def upsample2x(x, y):
+    nb, h, w, c = x.shape
+    capi.check(capi.lib().b2sd_op_upsample2x(x.data_ptr(), y.data_ptr(), nb, h, w, c, _sp()), "b2sd_op_upsample2x")
+    return y
+
+
+def smallconv(x, w_oihw, bias, y, *, flags=0):
+    """x: NHWC fp16 (or u8 when flags&1) [nb,in_h,in_w,cin]; y NHWC fp16 [nb,h,w,cout]."""
+    nb, in_h, in_w, cin = x.shape
+    _, h, w, cout = y.shape
+    capi.check(capi.lib().b2sd_op_smallconv(x.data_ptr(), w_oihw.data_ptr(), 0 if bias is None else bias.data_ptr(),
+                                            y.data_ptr(), y.stride(2), nb, h, w, cin, cout, in_h, in_w, flags, _sp()),
+               "b2sd_op_smallconv")
+    return y
+
+
+def lcm_step(x, eps, noise, coef, out_latent, do_add_noise=True):
+    T, hw = x.shape[0], x.shape[1] * x.shape[2]
+    capi.check(capi.lib().b2sd_op_lcm_step(x.data_ptr(), eps.data_ptr(), noise.data_ptr(), coef.data_ptr(),
+                                           out_latent.data_ptr(), T, hw, int(do_add_noise), _sp()), "b2sd_op_lcm_step")
+    return out_latent
+
+
+def post_u8(y, out):
+    nb, h, w, _ = y.shape
+    capi.check(capi.lib().b2sd_op_post_u8(y.data_ptr(), y.stride(2), out.data_ptr(), nb, h, w, _sp()), "b2sd_op_post_u8")
+    return out

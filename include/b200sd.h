@@ -68,6 +68,36 @@ typedef struct {
 int b2sd_op_igemm(const b2sd_igemm_desc* d, void* stream);
 uint64_t b2sd_igemm_partial_floats(int splits, int64_t rows_total, int n_valid);
 
+/* Flash attention (self / cross) of BasicTransformerBlock.attn1 / attn2 (inside unet.engine).
+ * q: [nb*sq][ldq], head h at columns [h*dp, (h+1)*dp); k likewise (batch b at row b*k_bstride, 0 = shared);
+ * vt = V^T: [heads*dp][ldvt] with the key index contiguous (batch b at column b*vt_bstride);
+ * out: [nb*sq][ldo], head h at columns [h*d_real, (h+1)*d_real). softmax scale = d_real^-0.5. */
+typedef struct {
+    const void* q; int ldq;
+    const void* k; int ldk; int64_t k_bstride; int64_t k_rows;
+    const void* vt; int ldvt; int64_t vt_bstride; int64_t vt_cols;
+    void* out; int ldo;
+    int nb, heads, sq, skv, d_real, dp;
+} b2sd_attn_desc;
+int b2sd_op_attention(const b2sd_attn_desc* d, void* stream);
+
+/* GroupNorm(+SiLU) over the channel concatenation [xa | xb] (xb may be NULL), NHWC fp16. */
+int b2sd_op_groupnorm(const void* xa, int ca, int lda, const void* xb, int cb, int ldb, const float* gamma,
+                      const float* beta, void* y, int ldy, int nb, int hw, int groups, float eps, int silu,
+                      void* stream);
+int b2sd_op_layernorm(const void* x, int ldx, const float* gamma, const float* beta, void* y, int ldy,
+                      int64_t rows, int c, float eps, void* stream);
+int b2sd_op_upsample2x(const void* x, void* y, int nb, int h, int w, int c, void* stream);
+/* direct 3x3 conv for Cin in {3,4}; flags: 1 = input is u8 NHWC scaled by 1/255 (lib/pipeline.py:61),
+ * 2 = tanh(x/3)*3 on the input (DecoderTiny), 4 = ReLU on the output */
+int b2sd_op_smallconv(const void* x, const void* w_oihw, const float* bias, void* y, int ldy, int nb, int h,
+                      int w, int cin, int cout, int in_h, int in_w, int flags, void* stream);
+/* StreamDiffusion scheduler_step_batch + stream-batch buffer update (see elementwise.cuh) */
+int b2sd_op_lcm_step(void* x, const void* eps, const void* noise, const float* coef, void* out_latent, int T,
+                     int hw, int do_add_noise, void* stream);
+/* decoder tail + lib/pipeline.py:72-74 on the fp16 grid -> u8 NCHW */
+int b2sd_op_post_u8(const void* y_nhwc, int ldy, void* out_nchw_u8, int nb, int h, int w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,8 @@ def describe_mismatch(got: torch.Tensor, ref: torch.Tensor, tol_abs: float, tol_
 
 
 def assert_close(got, ref, tol_abs, tol_rel, what=""):
-    err = (got.float() - ref.float()).abs()
-    ok = bool((err <= tol_abs + tol_rel * ref.float().abs()).all()) and not bool(torch.isnan(got.float()).any())
+    got = got.detach().float().cpu()
+    ref = ref.detach().float().cpu()
+    err = (got - ref).abs()
+    ok = bool((err <= tol_abs + tol_rel * ref.abs()).all()) and not bool(torch.isnan(got).any())
     assert ok, what + "\n" + describe_mismatch(got, ref, tol_abs, tol_rel)
