@@ -321,14 +321,23 @@ int attn_plan(const AttnDesc& d, AttnPlan* plan) {
     return 0;
 }
 
-int attn_launch(const AttnPlan& plan, cudaStream_t s) {
+int attn_init() {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(attn_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(attn_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(attn_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e1 = cudaFuncSetAttribute(attn_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e2 = cudaFuncSetAttribute(attn_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e3 = cudaFuncSetAttribute(attn_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+            b2_set_error("cudaFuncSetAttribute(attn) failed");
+            return -1;
+        }
         attr_set = true;
     }
+    return 0;
+}
+
+int attn_launch(const AttnPlan& plan, cudaStream_t s) {
+    if (attn_init()) return -1;
     const AttnDesc& d = plan.d;
     AttnParams p;
     p.tmq = plan.tmq; p.tmk = plan.tmk; p.tmv = plan.tmv;

@@ -36,5 +36,6 @@ struct AttnPlan {
 
 int attn_plan(const AttnDesc& d, AttnPlan* plan);
 int attn_launch(const AttnPlan& plan, cudaStream_t s);
+int attn_init();
 
 }  // namespace b2

@@ -211,7 +211,12 @@ __global__ void __launch_bounds__(256) smallconv_kernel(SmallConvArgs a) {
             for (int c = 0; c < CIN; ++c) {
                 float v = 0.f;
                 if (in) {
-                    if (a.flags & SC_IN_U8) {
+                    if (a.flags & (SC_IN_F32_NCHW | SC_IN_F16_NCHW)) {
+                        // lib/pipeline.py:65 hands StreamDiffusion a (3,H,W) float tensor in [0,1]
+                        const long idx = (((long)n * CIN + c) * a.in_h + sy) * a.in_w + sx;
+                        v = (a.flags & SC_IN_F32_NCHW) ? reinterpret_cast<const float*>(a.x)[idx]
+                                                       : __half2float(reinterpret_cast<const __half*>(a.x)[idx]);
+                    } else if (a.flags & SC_IN_U8) {
                         // lib/pipeline.py:61 convertto(scale=1/255); the 2x-1 of VaeImageProcessor and the
                         // (x+1)/2 of EncoderTiny cancel
                         v = (float)reinterpret_cast<const uint8_t*>(a.x)[base + c] * (1.0f / 255.0f);
@@ -350,6 +355,24 @@ __global__ void post_u8_kernel(const __half* __restrict__ y, int ldy, uint8_t* _
         v = __hmax(zero, __hmin(v, s255));      // .clamp(0, 255)
         out[((long)n * 3 + c) * hw + q] = (uint8_t)__half2int_rz(v);  // .to(uint8): truncation
     }
+}
+
+__global__ void post_f16_kernel(const __half* __restrict__ y, int ldy, __half* __restrict__ out, int nb, int h, int w) {
+    const long hw = (long)h * w;
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (long)nb * hw) return;
+    const int n = (int)(p / hw);
+    const long q = p % hw;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        out[((long)n * 3 + c) * hw + q] = __hsub(__hmul(y[p * ldy + c], __float2half(2.0f)), __float2half(1.0f));
+}
+
+int post_f16_launch(const __half* y_nhwc, int ldy, __half* out_nchw, int nb, int h, int w, cudaStream_t s) {
+    const long total = (long)nb * h * w;
+    post_f16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(y_nhwc, ldy, out_nchw, nb, h, w);
+    B2_CHECK_LAUNCH("post_f16");
+    return 0;
 }
 
 int post_u8_launch(const __half* y_nhwc, int ldy, uint8_t* out_nchw, int nb, int h, int w, cudaStream_t s) {

@@ -29,7 +29,7 @@ int upsample2x_launch(const __half* x, __half* y, int nb, int h, int w, int c, c
 // Direct 3x3 conv (pad 1, stride 1) for tiny Cin (<= 4): UNet conv_in (4->320), TAESD encoder head
 // (3->64, reads the u8 NHWC video frame and applies 1/255), TAESD decoder head (4->64, tanh(z/3)*3 in,
 // ReLU out).  w: fp16 [cout][cin][3][3] (PyTorch OIHW), bias fp32 [cout] or null.
-enum : int { SC_IN_U8 = 1, SC_IN_TANH3 = 2, SC_OUT_RELU = 4 };
+enum : int { SC_IN_U8 = 1, SC_IN_TANH3 = 2, SC_OUT_RELU = 4, SC_IN_F32_NCHW = 8, SC_IN_F16_NCHW = 16 };
 struct SmallConvArgs {
     const void* x;       // fp16 NHWC [nb,h,w,cin] or u8 NHWC when SC_IN_U8
     const __half* w;
@@ -51,6 +51,8 @@ int lcm_step_launch(__half* x, const __half* eps, const __half* noise, const flo
 // Decoder tail + lib/pipeline.py:72-74 + image_utils.postprocess_image, on the fp16 grid:
 //   y16 (decoder conv out, fp16) -> y*2-1 -> /2+0.5 -> clamp(0,1) -> *255 -> clamp -> trunc to u8, NCHW
 int post_u8_launch(const __half* y_nhwc, int ldy, uint8_t* out_nchw, int nb, int h, int w, cudaStream_t s);
+// StreamDiffusion.__call__ return value: fp16 NCHW image = y*2-1 (DecoderTiny tail), roughly [-1,1]
+int post_f16_launch(const __half* y_nhwc, int ldy, __half* out_nchw, int nb, int h, int w, cudaStream_t s);
 
 // fp32 tiny linear for prepare-time work: out[b][n] = bias[n] + sum_k act(in[b][k]) * W[n][k]
 int small_linear_launch(const float* in, int in_ld, const __half* w, const float* bias, float* out, int out_ld,

@@ -483,7 +483,7 @@ int igemm_plan(const IgemmDesc& d, IgemmPlan* plan) {
     return 0;
 }
 
-int igemm_launch(const IgemmPlan& plan, cudaStream_t stream) {
+int igemm_init() {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -492,8 +492,14 @@ int igemm_launch(const IgemmPlan& plan, cudaStream_t stream) {
             b2_set_error("cudaFuncSetAttribute(igemm): %s", cudaGetErrorString(e));
             return -1;
         }
+        if (!get_encode()) return -1;
         attr_set = true;
     }
+    return 0;
+}
+
+int igemm_launch(const IgemmPlan& plan, cudaStream_t stream) {
+    if (igemm_init()) return -1;
     igemm_kernel<<<plan.grid, IG_THREADS, plan.smem, stream>>>(plan.p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

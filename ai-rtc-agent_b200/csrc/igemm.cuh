@@ -95,6 +95,8 @@ struct IgemmPlan {
 int igemm_plan(const IgemmDesc& d, IgemmPlan* plan);
 // Enqueue on stream (main kernel + split-K finalize if needed).
 int igemm_launch(const IgemmPlan& plan, cudaStream_t stream);
+// one-time function attributes / driver entry points (call outside stream capture)
+int igemm_init();
 // workspace floats needed for a split-K plan
 size_t igemm_partial_floats(int splits, long rows_total, int n_valid);
 const char* b2_last_error();

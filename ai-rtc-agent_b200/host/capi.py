@@ -43,6 +43,17 @@ class AttnDesc(C.Structure):
     ]
 
 
+class EngineConfig(C.Structure):
+    _fields_ = [
+        ("block_out_channels", C.c_int * 4), ("heads", C.c_int * 4), ("down_attn", C.c_int * 4),
+        ("cross_attention_dim", C.c_int), ("layers_per_block", C.c_int), ("norm_groups", C.c_int),
+        ("ctx_tokens", C.c_int), ("batch", C.c_int), ("height", C.c_int), ("width", C.c_int),
+        ("do_add_noise", C.c_int), ("use_cuda_graph", C.c_int),
+    ]
+
+
+IN_U8_NHWC, IN_F32_NCHW, IN_F16_NCHW = 0, 1, 2
+OUT_U8_NCHW, OUT_F16_NCHW = 0, 1
 IG_RELU = 1
 IG_GEGLU = 2
 
@@ -71,6 +82,19 @@ def lib() -> C.CDLL:
         _lib.b2sd_op_smallconv.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
         _lib.b2sd_op_lcm_step.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, vp]
         _lib.b2sd_op_post_u8.argtypes = [vp, ci, vp, ci, ci, ci, vp]
+        _lib.b2sd_create.argtypes = [C.POINTER(EngineConfig), C.POINTER(vp)]
+        _lib.b2sd_destroy.argtypes = [vp]
+        _lib.b2sd_load_tensor.argtypes = [vp, C.c_char_p, vp, ci, C.POINTER(i64), ci]
+        _lib.b2sd_prepare.argtypes = [vp, vp, vp, vp, vp, vp]
+        _lib.b2sd_set_prompt_embeds.argtypes = [vp, vp, vp]
+        _lib.b2sd_set_timesteps.argtypes = [vp, vp, vp]
+        _lib.b2sd_step.argtypes = [vp, vp, ci, ci, vp, vp]
+        _lib.b2sd_step_ex.argtypes = [vp, vp, ci, ci, ci, vp, ci, vp]
+        _lib.b2sd_get_tensor.argtypes = [vp, C.c_char_p, vp, i64, C.POINTER(i64), C.POINTER(ci), vp]
+        _lib.b2sd_launches_per_step.argtypes = [vp]
+        for name in ("create", "destroy", "load_tensor", "prepare", "set_prompt_embeds", "set_timesteps", "step",
+                     "step_ex", "get_tensor", "launches_per_step"):
+            getattr(_lib, "b2sd_" + name).restype = C.c_int
         for name in ("attention", "groupnorm", "layernorm", "upsample2x", "smallconv", "lcm_step", "post_u8"):
             getattr(_lib, "b2sd_op_" + name).restype = C.c_int
     return _lib

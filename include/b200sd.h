@@ -98,6 +98,72 @@ int b2sd_op_lcm_step(void* x, const void* eps, const void* noise, const float* c
 /* decoder tail + lib/pipeline.py:72-74 on the fp16 grid -> u8 NCHW */
 int b2sd_op_post_u8(const void* y_nhwc, int ldy, void* out_nchw_u8, int nb, int h, int w, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Engine level: one handle == one temporal stream (one StreamDiffusion instance, lib/wrapper.py:168).
+ * Replaces StreamDiffusion + UNet2DConditionModelEngine + AutoencoderKLEngine
+ * (lib/wrapper.py:445-466, 494-504) for mode="img2img", use_denoising_batch=True, frame_buffer_size=1,
+ * cfg_type="self" with guidance_scale <= 1 (the only configuration lib/pipeline.py:23-42 builds).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct b2sd_engine* b2sd_handle;
+
+typedef struct {
+    int block_out_channels[4];   /* (320,640,1280,1280) */
+    int heads[4];                /* SD-1.5: 8,8,8,8   SD-Turbo: 5,10,20,20 */
+    int down_attn[4];            /* 1,1,1,0 */
+    int cross_attention_dim;     /* 768 | 1024 */
+    int layers_per_block;        /* 2 */
+    int norm_groups;             /* 32 */
+    int ctx_tokens;              /* 77 */
+    int batch;                   /* len(t_index_list) * frame_buffer_size (lib/wrapper.py:159-163) */
+    int height, width;           /* image size, multiples of 64 */
+    int do_add_noise;            /* lib/wrapper.py:53 */
+    int use_cuda_graph;          /* replay the frame program as one CUDA graph */
+} b2sd_config;
+
+int b2sd_create(const b2sd_config* cfg, b2sd_handle* out);
+int b2sd_destroy(b2sd_handle h);
+
+/* Weights under diffusers state-dict names: UNet keys as-is ("down_blocks.0.resnets.0.conv1.weight"),
+ * TAESD keys prefixed "vae." ("vae.encoder.layers.0.weight").  ptr may be host or device memory.
+ * dtype: 0 = fp16, 1 = fp32.  Replaces the ONNX export + TensorRT build of lib/wrapper.py:785-910. */
+int b2sd_load_tensor(b2sd_handle h, const char* key, const void* ptr, int dtype, const int64_t* shape, int ndim);
+
+/* StreamDiffusion.prepare (via lib/wrapper.py:197-234): fixes per-slot scalars and noise, zeroes the
+ * stream-batch latent buffer, builds the frame program.  All pointers are HOST memory:
+ *   prompt_embeds  fp16 [ctx_tokens][cross_attention_dim]   (CLIP output, encoded by the caller)
+ *   timesteps      fp32 [batch]                             (sub_timesteps_tensor)
+ *   coef           fp32 [4][batch] = alpha_prod_t_sqrt, beta_prod_t_sqrt, c_skip, c_out
+ *   init_noise     fp16 [batch][4][h/8][w/8]                (NCHW, as torch.randn produced it)
+ * Synchronises `stream`. */
+int b2sd_prepare(b2sd_handle h, const void* prompt_embeds, const float* timesteps, const float* coef,
+                 const void* init_noise, void* stream);
+/* StreamDiffusion.update_prompt (lib/pipeline.py:44-45): refresh the per-layer cross-attention K/V cache */
+int b2sd_set_prompt_embeds(b2sd_handle h, const void* prompt_embeds, void* stream);
+/* lib/wrapper.py:389-407 update_t_index_list: only sub_timesteps change (alpha/beta/c_skip/c_out keep the
+ * values given to b2sd_prepare -- reference behaviour) */
+int b2sd_set_timesteps(b2sd_handle h, const float* timesteps, void* stream);
+
+/* One StreamDiffusionPipeline.__call__ (lib/pipeline.py:76-96, NVENC branch): frame_in = device u8 NHWC
+ * [in_h][in_w][3] (nearest-resized to height x width if different, SURVEY a-4), frame_out = device u8 NCHW
+ * [3][height][width].  Enqueues on `stream`; no host synchronisation. */
+int b2sd_step(b2sd_handle h, const void* frame_in, int in_h, int in_w, void* frame_out, void* stream);
+
+/* Same, for the reference's split call path preprocess -> predict -> postprocess (lib/pipeline.py:50-74):
+ * input may be the (3,H,W) float tensor lib/pipeline.py:65 produces; output may be the fp16 NCHW image
+ * in [-1,1] that StreamDiffusion.__call__ returns (lib/wrapper.py:330). */
+enum { B2SD_IN_U8_NHWC = 0, B2SD_IN_F32_NCHW = 1, B2SD_IN_F16_NCHW = 2 };
+enum { B2SD_OUT_U8_NCHW = 0, B2SD_OUT_F16_NCHW = 1 };
+int b2sd_step_ex(b2sd_handle h, const void* frame_in, int in_kind, int in_h, int in_w, void* frame_out,
+                 int out_kind, void* stream);
+
+/* Parity/debug taps: copies a named intermediate of the last step to host memory as fp16 NHWC.
+ * Names: "x_t", "unet_in", "eps", "x0", "image", "conv_in", "down.I.J", "mid", "up.I.J".
+ * Returns the element count via *count (pass dst = NULL to query).  Synchronises `stream`. */
+int b2sd_get_tensor(b2sd_handle h, const char* name, void* dst, int64_t capacity, int64_t* count, int* dims4,
+                    void* stream);
+/* number of kernel launches (graph nodes) in one b2sd_step */
+int b2sd_launches_per_step(b2sd_handle h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,168 @@
+"""End-to-end GPU parity of the engine (through the C ABI, via host/stream.py) against the fp32 CPU oracle on
+identical seeded weights, prompt embeddings, noise and frames.
+
+Stated tolerances (the reference has no pins of its own -- parity unpinned):
+  * latents / activations vs the fp32 oracle:  max|d| <= 2e-2 * max|ref|  and cosine >= 0.999
+  * final u8 image:  |d| <= 2 LSB on >= 99.9 % of pixels, max |d| <= 8
+(fp16 storage of every activation with fp32 accumulation, like the reference's fp16 TensorRT engines.)"""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _cmp(name, got_nhwc, ref_nchw, rows):
+    got = got_nhwc.float().permute(0, 3, 1, 2)
+    ref = ref_nchw.float()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-12
+    cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
+    rows.append((name, tuple(ref.shape), err / scale, cos))
+    return err / scale, cos
+
+
+def _build(arch_name, turbo, t_index_list, hw, cuda, seed=0):
+    from ai_rtc_agent_b200.host import arch as A
+    from ai_rtc_agent_b200.host.stream import StreamDiffusion
+    from oracle import stream as ostream
+    from oracle import unet as ounet
+    from oracle import weights as ow
+    if arch_name == "tiny":
+        cfg, arch = ounet.tiny_config(turbo), (A.TINY_TURBO if turbo else A.TINY_SD15)
+    else:
+        cfg, arch = (ounet.SD_TURBO, A.SD_TURBO) if turbo else (ounet.SD15, A.SD15)
+    usd16 = ow.make_unet_weights(cfg)
+    vsd16 = ow.make_taesd_weights()
+    emb = ow.make_prompt_embeds(cfg.cross_attention_dim)
+    sd = StreamDiffusion(arch, usd16, vsd16, t_index_list, lambda p: emb, width=hw, height=hw, device="cuda",
+                         use_cuda_graph=bool(int(os.getenv("B200SD_TEST_GRAPH", "1"))))
+    sd.prepare("p", guidance_scale=0.0)
+    orc = ostream.StreamOracle(ow.to_float(usd16), cfg, ow.to_float(vsd16), t_index_list, hw, hw)
+    orc.prepare(emb.float(), guidance_scale=0.0, init_noise=sd.init_noise.float())
+    return sd, orc
+
+
+def _u8_check(got, ref, what):
+    d = (got.cpu().int() - ref.cpu().int()).abs()
+    frac = (d <= 2).float().mean().item()
+    assert frac >= 0.999 and d.max().item() <= 8, f"{what}: frac(|d|<=2)={frac:.5f} max={d.max().item()} mean={d.float().mean().item():.3f}"
+    return frac, d.max().item()
+
+
+@pytest.mark.parametrize("turbo", [True, False])
+def test_tiny_unet_taps_single_step(cuda, turbo):
+    """Layer-by-layer: every UNet block output, eps, x0, decoded image of one frame (T=1)."""
+    from oracle import pipeline as opipe
+    from oracle import unet as ounet
+    from oracle import weights as ow
+    sd, orc = _build("tiny", turbo, [32], 128, cuda)
+    frame = ow.make_frame(128, 128, seed=0)
+    out = sd.step_u8(frame.to(cuda))
+    ref_u8 = opipe.frame_to_u8(orc, frame)
+    taps = {}
+    ounet.unet_forward(orc.unet_sd, orc.cfg, orc.last["unet_in"], orc.sub_timesteps_tensor, orc.prompt_embeds, taps)
+    rows = []
+    worst = 0.0
+    _cmp("x_t", sd.get_tensor("x_t"), orc.last["x_t"], rows)
+    for name, ref in taps.items():
+        e, c = _cmp(name, sd.get_tensor(name), ref, rows)
+        worst = max(worst, e)
+    _cmp("eps", sd.get_tensor("eps"), orc.last["eps"], rows)
+    _cmp("x0", sd.get_tensor("x0"), orc.last["x0"], rows)
+    img = sd.get_tensor("image")  # decoder conv output y; oracle image = 2y-1
+    _cmp("image", img * 2 - 1, orc.last["image"], rows)
+    table = "\n".join(f"{n:12s} {str(s):22s} relerr={e:.2e} cos={c:.6f}" for n, s, e, c in rows)
+    print(table)
+    for n, s, e, c in rows:
+        assert e <= 2e-2 and c >= 0.999, "tap " + n + " out of tolerance\n" + table
+    _u8_check(out, ref_u8, "tiny u8 frame")
+
+
+@pytest.mark.parametrize("turbo,t_index_list", [(True, [32]), (False, [18, 26, 35, 45])])
+def test_tiny_stream_loop(cuda, turbo, t_index_list):
+    """8 consecutive frames through the stream-batch loop: u8 outputs (incl. the T-1 frame output lag) and the
+    x_t_latent_buffer state must track the oracle frame by frame."""
+    from oracle import pipeline as opipe
+    from oracle import weights as ow
+    sd, orc = _build("tiny", turbo, t_index_list, 128, cuda)
+    T = len(t_index_list)
+    for i in range(8):
+        frame = ow.make_frame(128, 128, seed=i)
+        out = sd.step_u8(frame.to(cuda))
+        ref = opipe.frame_to_u8(orc, frame)
+        _u8_check(out, ref, f"frame {i}")
+        if T > 1:
+            buf = sd.get_tensor("unet_in")[1:]  # after the step: slots 1.. hold the re-noised x0 of slots 0..T-2
+            rows = []
+            e, c = _cmp("buffer", buf, orc.x_t_latent_buffer, rows)
+            assert e <= 2e-2 and c >= 0.999, f"frame {i}: x_t_latent_buffer relerr {e:.3e} cos {c:.6f}"
+
+
+def test_tiny_graph_equals_eager(cuda, monkeypatch):
+    """CUDA-graph replay and plain launches of the same program give bit-identical frames."""
+    from oracle import weights as ow
+    outs = []
+    for g in ("1", "0"):
+        monkeypatch.setenv("B200SD_TEST_GRAPH", g)
+        sd, _ = _build("tiny", True, [10, 30], 128, cuda)
+        frames = [sd.step_u8(ow.make_frame(128, 128, seed=i).to(cuda)).cpu() for i in range(4)]
+        outs.append(frames)
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
+def test_tiny_update_prompt_and_t_index(cuda):
+    """update_prompt refreshes the cross-attention K/V cache; update_t_index_list changes only the timestep
+    embedding (lib/wrapper.py:389-407 quirk) -- both must track the oracle."""
+    from oracle import pipeline as opipe
+    from oracle import weights as ow
+    from ai_rtc_agent_b200.host.wrapper import StreamDiffusionWrapper
+    sd, orc = _build("tiny", True, [20, 40], 128, cuda)
+    emb2 = ow.make_prompt_embeds(orc.cfg.cross_attention_dim, seed=77)
+    sd.prompt_encoder = lambda p: emb2
+    sd.update_prompt("another prompt")
+    orc.update_prompt_embeds(emb2.float())
+    w = StreamDiffusionWrapper.__new__(StreamDiffusionWrapper)  # reuse the reference-shaped method on this stream
+    w.stream, w.device = sd, "cuda"
+    w.update_t_index_list([5, 45])
+    orc.update_t_index_list([5, 45])
+    assert sd.sub_timesteps == orc.sub_timesteps == [899, 99]
+    for i in range(3):
+        frame = ow.make_frame(128, 128, seed=10 + i)
+        _u8_check(sd.step_u8(frame.to(cuda)), opipe.frame_to_u8(orc, frame), f"frame {i} after updates")
+
+
+def test_resize_and_float_entry(cuda):
+    """Non-native frame size -> nearest resize (VaeImageProcessor); float (3,H,W) entry == u8 entry."""
+    from oracle import pipeline as opipe
+    from oracle import weights as ow
+    sd, orc = _build("tiny", True, [32], 128, cuda)
+    frame = ow.make_frame(96, 160, seed=3)
+    out = sd.step_u8(frame.to(cuda))
+    ref = opipe.frame_to_u8(orc, frame)
+    _u8_check(out, ref, "resized frame")
+    x = (frame.to(cuda).float() / 255.0).permute(0, 3, 1, 2).squeeze(0)
+    img = sd(x)  # (1,3,H,W) fp16 in [-1,1]
+    u8 = ((img / 2 + 0.5).clamp(0, 1)[0] * 255.0).clamp(0, 255).to(torch.uint8)[None]
+    assert torch.equal(u8, out)
+
+
+@pytest.mark.parametrize("turbo,t_index_list,hw,nframes", [
+    (True, [32], 512, 2),                  # BASELINE config 2: SD-Turbo 1-step 512x512
+    (False, [18, 26, 35, 45], 256, 5),     # SD-1.5 + 4-step stream batch (config 3 arch) at 256 for oracle speed
+])
+def test_full_width_models(cuda, turbo, t_index_list, hw, nframes):
+    from oracle import pipeline as opipe
+    from oracle import weights as ow
+    sd, orc = _build("full", turbo, t_index_list, hw, cuda)
+    for i in range(nframes):
+        frame = ow.make_frame(hw, hw, seed=i)
+        out = sd.step_u8(frame.to(cuda))
+        ref = opipe.frame_to_u8(orc, frame)
+        rows = []
+        e, c = _cmp("eps", sd.get_tensor("eps"), orc.last["eps"], rows)
+        frac, mx = _u8_check(out, ref, f"frame {i}")
+        print(f"frame {i}: eps relerr {e:.2e} cos {c:.6f}; u8 frac(|d|<=2) {frac:.5f} max {mx}")
+        assert e <= 2e-2 and c >= 0.999
