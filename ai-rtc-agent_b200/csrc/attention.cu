@@ -13,7 +13,9 @@ namespace b2 {
 constexpr int AT_BQ = 128;      // query rows per CTA == UMMA M
 constexpr int AT_STAGES = 2;    // K/V ring depth
 constexpr int AT_THREADS = 192; // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2-5 softmax
-constexpr uint32_t AT_TMEM_S0 = 0, AT_TMEM_S1 = 128, AT_TMEM_O = 256, AT_TMEM_COLS = 512;
+// TMEM: S (one QK^T tile, BKV columns) at column 0, O accumulator (DP columns) right after it; 256 columns per
+// CTA so that two CTAs share an SM (one's softmax overlaps the other's MMAs).
+constexpr uint32_t AT_TMEM_COLS = 256;
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -48,9 +50,9 @@ __global__ void __launch_bounds__(AT_THREADS) attn_kernel(const __grid_constant_
     uint64_t* q_full = bars;
     uint64_t* kv_full = bars + 1;               // [AT_STAGES]
     uint64_t* kv_empty = kv_full + AT_STAGES;   // [AT_STAGES]
-    uint64_t* s_full = kv_empty + AT_STAGES;    // [2]
-    uint64_t* s_empty = s_full + 2;             // [2]
-    uint64_t* p_full = s_empty + 2;
+    uint64_t* s_full = kv_empty + AT_STAGES;
+    uint64_t* s_empty = s_full + 1;
+    uint64_t* p_full = s_empty + 1;
     uint64_t* o_done = p_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
 
@@ -72,10 +74,8 @@ __global__ void __launch_bounds__(AT_THREADS) attn_kernel(const __grid_constant_
             mbar_init(&kv_full[s], 1);
             mbar_init(&kv_empty[s], 1);
         }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&s_full[s], 1);
-            mbar_init(&s_empty[s], 128);
-        }
+        mbar_init(s_full, 1);
+        mbar_init(s_empty, 128);
         mbar_init(p_full, 128);
         mbar_init(o_done, 1);
         fence_mbar_init();
@@ -120,10 +120,10 @@ __global__ void __launch_bounds__(AT_THREADS) attn_kernel(const __grid_constant_
             auto issue_qk = [&](int j) {
                 const int st = j % AT_STAGES;
                 mbar_wait(&kv_full[st], (j / AT_STAGES) & 1);
-                mbar_wait(&s_empty[j & 1], ((j >> 1) & 1) ^ 1);
+                mbar_wait(s_empty, (j & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t sk = smem_u32(sKV + st * STAGE_BYTES);
-                const uint32_t tS = tmem_base + ((j & 1) ? AT_TMEM_S1 : AT_TMEM_S0);
+                const uint32_t tS = tmem_base;
 #pragma unroll
                 for (int a = 0; a < DA; ++a) {
                     const uint64_t dq = make_kmajor_sw128_desc(smem_u32(sQ) + a * (AT_BQ * 128));
@@ -132,12 +132,12 @@ __global__ void __launch_bounds__(AT_THREADS) attn_kernel(const __grid_constant_
                     for (int k = 0; k < 4; ++k)
                         umma_f16(tS, dq + 2 * k, dk + 2 * k, idesc_s, (a | k) ? 1u : 0u);
                 }
-                umma_commit(&s_full[j & 1]);
+                umma_commit(s_full);
             };
             mbar_wait(q_full, 0);
             issue_qk(0);
             for (int j = 0; j < nblk; ++j) {
-                if (j + 1 < nblk) issue_qk(j + 1);  // overlaps softmax(j)
+                if (j + 1 < nblk) issue_qk(j + 1);  // issues as soon as softmax(j) has drained S; overlaps its P stores
                 const int st = j % AT_STAGES;
                 mbar_wait(p_full, j & 1);
                 tc_fence_after();
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_kernel(const __grid_constant_
                     const uint64_t dv = make_kmajor_sw128_desc(sv + a * (DP * 128));
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_f16(tmem_base + AT_TMEM_O, dp + 2 * k, dv + 2 * k, idesc_o,
+                        umma_f16(tmem_base + BKV, dp + 2 * k, dv + 2 * k, idesc_o,
                                  (j > 0 || a > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(o_done);
@@ -161,10 +161,12 @@ __global__ void __launch_bounds__(AT_THREADS) attn_kernel(const __grid_constant_
         const int r = q * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         float m_run = -INFINITY, l_run = 0.f;
+        const uint32_t tS = lane_addr;
+        const uint32_t tO = lane_addr + BKV;
         for (int j = 0; j < nblk; ++j) {
-            const uint32_t tS = lane_addr + ((j & 1) ? AT_TMEM_S1 : AT_TMEM_S0);
             const int kv_valid = p.skv - j * BKV;  // columns >= kv_valid are masked
-            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+            const bool full = kv_valid >= BKV;     // warp-uniform: interior blocks skip all masking
+            mbar_wait(s_full, j & 1);
             tc_fence_after();
             // pass 1: row max
             float mx = -INFINITY;
@@ -173,9 +175,14 @@ __global__ void __launch_bounds__(AT_THREADS) attn_kernel(const __grid_constant_
                 uint32_t v[32];
                 tmem_ld32(tS + c, v);
                 tmem_ld_wait();
+                if (full) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (c + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+                }
             }
             const float m_new = fmaxf(m_run, mx * p.scale_log2);
             const float alpha = ex2_approx(m_run - m_new);
@@ -190,12 +197,15 @@ __global__ void __launch_bounds__(AT_THREADS) attn_kernel(const __grid_constant_
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                    float p0 = (c + i < kv_valid) ? ex2_approx(__uint_as_float(v[i]) * p.scale_log2 - m_new) : 0.f;
-                    float p1 = (c + i + 1 < kv_valid) ? ex2_approx(__uint_as_float(v[i + 1]) * p.scale_log2 - m_new) : 0.f;
-                    __half2 hp = __floats2half2_rn(p0, p1);
-                    const float2 back = __half22float2(hp);
-                    rs += back.x + back.y;  // normaliser sums exactly what the MMA consumes
-                    pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hp);
+                    float p0 = ex2_approx(__uint_as_float(v[i]) * p.scale_log2 - m_new);
+                    float p1 = ex2_approx(__uint_as_float(v[i + 1]) * p.scale_log2 - m_new);
+                    if (!full) {
+                        if (c + i >= kv_valid) p0 = 0.f;
+                        if (c + i + 1 >= kv_valid) p1 = 0.f;
+                    }
+                    rs += p0 + p1;
+                    const __half2 hp = __floats2half2_rn(p0, p1);
+                    pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
                 }
                 const int atom = c >> 6;
                 uint8_t* prow = sP + atom * (AT_BQ * 128);
@@ -206,9 +216,9 @@ __global__ void __launch_bounds__(AT_THREADS) attn_kernel(const __grid_constant_
                         make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
                 }
             }
-            // S(j) fully consumed
+            // S(j) fully consumed: the next QK^T may overwrite it
             tc_fence_before();
-            mbar_arrive(&s_empty[j & 1]);
+            mbar_arrive(s_empty);
             // rescale the running O accumulator (TMEM) when any row of this warp moved its max
             if (j > 0) {
                 const bool need = __any_sync(0xffffffffu, alpha != 1.0f);
@@ -216,11 +226,11 @@ __global__ void __launch_bounds__(AT_THREADS) attn_kernel(const __grid_constant_
 #pragma unroll
                     for (int c = 0; c < DP; c += 32) {
                         uint32_t v[32];
-                        tmem_ld32(lane_addr + AT_TMEM_O + c, v);
+                        tmem_ld32(tO + c, v);
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-                        tmem_st32(lane_addr + AT_TMEM_O + c, v);
+                        tmem_st32(tO + c, v);
                     }
                     tmem_st_wait();
                 }
@@ -240,7 +250,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_kernel(const __grid_constant_
 #pragma unroll
         for (int c = 0; c < DP; c += 32) {
             uint32_t v[32];
-            tmem_ld32(lane_addr + AT_TMEM_O + c, v);
+            tmem_ld32(lane_addr + BKV + c, v);
             tmem_ld_wait();
             if (row_ok) {
 #pragma unroll

@@ -78,6 +78,18 @@ int b2sd_op_groupnorm(const void* xa, int ca, int lda, const void* xb, int cb, i
     a.gamma = gamma; a.beta = beta;
     a.y = reinterpret_cast<__half*>(y); a.ldy = ldy;
     a.nb = nb; a.hw = hw; a.groups = groups; a.eps = eps; a.silu = silu;
+    static float* scratch = nullptr;   // op-level entry only (tests); the engine passes its own workspace
+    static size_t scratch_floats = 0;
+    const size_t need = groupnorm_partial_floats(nb, groups);
+    if (need > scratch_floats) {
+        if (scratch) cudaFree(scratch);
+        if (cudaMalloc(&scratch, need * sizeof(float)) != cudaSuccess) {
+            b2_set_error("b2sd_op_groupnorm: cudaMalloc failed");
+            return -1;
+        }
+        scratch_floats = need;
+    }
+    a.partial = scratch;
     return groupnorm_launch(a, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -36,57 +36,155 @@ __device__ __forceinline__ T block_reduce_sum(T v, T* scratch) {
 }
 
 // ------------------------------------------------------------------------------------------ GroupNorm
-// one CTA per (group, batch item); two passes over an L2-resident slab (stats, then normalise+SiLU)
-__global__ void __launch_bounds__(512) groupnorm_kernel(GroupNormArgs a) {
-    __shared__ float scratch[32];
-    const int g = blockIdx.x, b = blockIdx.y;
+// Pass 1: grid (chunks, nb); a CTA owns `ppc` consecutive pixels x all channels (fully coalesced 16-byte
+// loads), reduces per channel, then per group, and writes one (sum, sumsq) pair per (chunk, group).
+// Pass 2: every CTA re-derives mean/rstd of its batch item from the <=128 chunk partials (fixed summation
+// order => deterministic), then normalises 8 channels per thread.
+constexpr int GN_MAX_CHUNKS = 128;
+
+__global__ void __launch_bounds__(512) gn_stats_kernel(GroupNormArgs a, int ppc, int vc, int rpi) {
+    extern __shared__ float sm[];  // [rpi][C][2] then reused as [C][2]
     const int C = a.ca + a.cb;
-    const int cpg = C / a.groups;
-    const int hp = cpg >> 1;  // half2 per pixel in this group
-    const long total = (long)a.hw * hp;
-    const int cbase = g * cpg;
-    float s = 0.f, ss = 0.f;
-    for (long e = threadIdx.x; e < total; e += blockDim.x) {
-        const int p = (int)(e / hp);
-        const int c = cbase + 2 * (int)(e % hp);
-        const __half2 v = (c < a.ca)
-                              ? *reinterpret_cast<const __half2*>(a.xa + ((long)b * a.hw + p) * a.lda + c)
-                              : *reinterpret_cast<const __half2*>(a.xb + ((long)b * a.hw + p) * a.ldb + (c - a.ca));
-        const float2 f = __half22float2(v);
-        s += f.x + f.y;
-        ss += f.x * f.x + f.y * f.y;
-    }
-    s = block_reduce_sum(s, scratch);
-    ss = block_reduce_sum(ss, scratch);
-    const float inv_n = 1.0f / (float)(a.hw * (long)cpg);
-    const float mean = s * inv_n;
-    const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + a.eps);
-    for (long e = threadIdx.x; e < total; e += blockDim.x) {
-        const int p = (int)(e / hp);
-        const int c = cbase + 2 * (int)(e % hp);
-        const __half2 v = (c < a.ca)
-                              ? *reinterpret_cast<const __half2*>(a.xa + ((long)b * a.hw + p) * a.lda + c)
-                              : *reinterpret_cast<const __half2*>(a.xb + ((long)b * a.hw + p) * a.ldb + (c - a.ca));
-        const float2 f = __half22float2(v);
-        float y0 = (f.x - mean) * rstd * a.gamma[c] + a.beta[c];
-        float y1 = (f.y - mean) * rstd * a.gamma[c + 1] + a.beta[c + 1];
-        if (a.silu) {
-            y0 = silu_f(y0);
-            y1 = silu_f(y1);
+    const int chunk = blockIdx.x, b = blockIdx.y;
+    const int col = threadIdx.x % vc;       // 8-channel vector column
+    const int prow = threadIdx.x / vc;      // pixel row inside one iteration
+    const int c0 = col * 8;
+    const bool from_a = c0 < a.ca;
+    const __half* base = from_a ? a.xa + c0 : a.xb + (c0 - a.ca);
+    const int ld = from_a ? a.lda : a.ldb;
+    const int p_begin = chunk * ppc;
+    const int p_end = min(a.hw, p_begin + ppc);
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+    if (prow < rpi) {
+        for (int p = p_begin + prow; p < p_end; p += rpi) {
+            const uint4 u = *reinterpret_cast<const uint4*>(base + ((long)b * a.hw + p) * ld);
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(h[i]);
+                s[2 * i] += f.x; q[2 * i] += f.x * f.x;
+                s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
+            }
         }
-        *reinterpret_cast<__half2*>(a.y + ((long)b * a.hw + p) * a.ldy + c) = __floats2half2_rn(y0, y1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            sm[((long)prow * C + c0 + i) * 2] = s[i];
+            sm[((long)prow * C + c0 + i) * 2 + 1] = q[i];
+        }
+    }
+    __syncthreads();
+    // reduce over pixel rows, then over the channels of each group
+    const int cpg = C / a.groups;
+    for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
+        float gs = 0.f, gq = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c)
+            for (int r = 0; r < rpi; ++r) {
+                gs += sm[((long)r * C + c) * 2];
+                gq += sm[((long)r * C + c) * 2 + 1];
+            }
+        float* dst = a.partial + (((long)b * GN_MAX_CHUNKS + chunk) * a.groups + g) * 2;
+        dst[0] = gs;
+        dst[1] = gq;
     }
 }
 
+__global__ void __launch_bounds__(256) gn_apply_kernel(GroupNormArgs a, int nchunks, long vec_per_batch) {
+    __shared__ float s_mean[64], s_rstd[64];
+    const int C = a.ca + a.cb;
+    const int b = blockIdx.y;
+    const int cpg = C / a.groups;
+    if (threadIdx.x < a.groups) {
+        float gs = 0.f, gq = 0.f;
+        const float* src = a.partial + ((long)b * GN_MAX_CHUNKS * a.groups + threadIdx.x) * 2;
+        for (int k = 0; k < nchunks; ++k) {
+            gs += src[(long)k * a.groups * 2];
+            gq += src[(long)k * a.groups * 2 + 1];
+        }
+        const float inv_n = 1.0f / ((float)a.hw * (float)cpg);
+        const float mean = gs * inv_n;
+        const float var = fmaxf(gq * inv_n - mean * mean, 0.f);
+        s_mean[threadIdx.x] = mean;
+        s_rstd[threadIdx.x] = rsqrtf(var + a.eps);
+    }
+    __syncthreads();
+    const int vc = C / 8;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < vec_per_batch; e += (long)gridDim.x * blockDim.x) {
+        const int col = (int)(e % vc);
+        const long p = e / vc;
+        const int c0 = col * 8;
+        const bool from_a = c0 < a.ca;
+        const __half* src = from_a ? a.xa + ((long)b * a.hw + p) * a.lda + c0
+                                   : a.xb + ((long)b * a.hw + p) * a.ldb + (c0 - a.ca);
+        const uint4 u = *reinterpret_cast<const uint4*>(src);
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+        const float4 g0 = *reinterpret_cast<const float4*>(a.gamma + c0);
+        const float4 g1 = *reinterpret_cast<const float4*>(a.gamma + c0 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(a.beta + c0);
+        const float4 b1 = *reinterpret_cast<const float4*>(a.beta + c0 + 4);
+        const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bet[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(h[i]);
+            x[2 * i] = f.x;
+            x[2 * i + 1] = f.y;
+        }
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+            const int ga = (c0 + i) / cpg, gb = (c0 + i + 1) / cpg;
+            float y0 = (x[i] - s_mean[ga]) * s_rstd[ga] * gam[i] + bet[i];
+            float y1 = (x[i + 1] - s_mean[gb]) * s_rstd[gb] * gam[i + 1] + bet[i + 1];
+            if (a.silu) {
+                y0 = silu_f(y0);
+                y1 = silu_f(y1);
+            }
+            oh[i >> 1] = __floats2half2_rn(y0, y1);
+        }
+        *reinterpret_cast<uint4*>(a.y + ((long)b * a.hw + p) * a.ldy + c0) = o;
+    }
+}
+
+size_t groupnorm_partial_floats(int nb, int groups) { return (size_t)nb * GN_MAX_CHUNKS * groups * 2; }
+
 int groupnorm_launch(const GroupNormArgs& a, cudaStream_t s) {
     const int C = a.ca + a.cb;
-    if (C % a.groups != 0 || ((C / a.groups) & 1) || (a.ca & 1) || (a.lda & 1) || (a.cb && (a.ldb & 1)) || (a.ldy & 1)) {
-        b2_set_error("groupnorm: unsupported channels %d+%d groups %d", a.ca, a.cb, a.groups);
+    if (C % a.groups != 0 || a.groups > 64 || (C & 7) || (a.ca & 7) || (a.lda & 7) || (a.cb && (a.ldb & 7)) || (a.ldy & 7) ||
+        !a.partial) {
+        b2_set_error("groupnorm: unsupported channels %d+%d groups %d (need multiples of 8 and a workspace)", a.ca, a.cb,
+                     a.groups);
         return -1;
     }
-    groupnorm_kernel<<<dim3(a.groups, a.nb), 512, 0, s>>>(a);
-    B2_CHECK_LAUNCH("groupnorm");
+    const int vc = C / 8;
+    if (vc > 512) {
+        b2_set_error("groupnorm: %d channels exceed one CTA row", C);
+        return -1;
+    }
+    int rpi = 512 / vc;            // pixel rows per iteration
+    if (rpi > 8) rpi = 8;
+    int ppc = (a.hw + GN_MAX_CHUNKS - 1) / GN_MAX_CHUNKS;
+    if (ppc < 1) ppc = 1;
+    if (rpi > ppc) rpi = ppc;
+    const int nchunks = (a.hw + ppc - 1) / ppc;
+    const int threads = ((vc * rpi + 31) / 32) * 32;
+    const size_t smem = (size_t)rpi * C * 2 * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr = true;
+    }
+    gn_stats_kernel<<<dim3(nchunks, a.nb), threads, smem, s>>>(a, ppc, vc, rpi);
+    B2_CHECK_LAUNCH("gn_stats");
+    const long vec_per_batch = (long)a.hw * vc;
+    long blocks = (vec_per_batch + 255) / 256;
+    const long cap = (148 * 4 + a.nb - 1) / a.nb;
+    if (blocks > cap) blocks = cap;
+    gn_apply_kernel<<<dim3((unsigned)blocks, a.nb), 256, 0, s>>>(a, nchunks, vec_per_batch);
+    B2_CHECK_LAUNCH("gn_apply");
     return 0;
 }
 

@@ -16,8 +16,11 @@ struct GroupNormArgs {
     int nb, hw, groups;
     float eps;
     int silu;
+    float* partial;   // workspace: groupnorm_partial_floats(nb, groups) floats (per-chunk group sums)
 };
+// two launches: coalesced per-chunk statistics, then normalise (+SiLU); both fill the whole GPU
 int groupnorm_launch(const GroupNormArgs& a, cudaStream_t s);
+size_t groupnorm_partial_floats(int nb, int groups);
 
 // LayerNorm over the last dim of [rows][c] fp16 (eps 1e-5, affine), one warp per row.
 int layernorm_launch(const __half* x, int ldx, const float* gamma, const float* beta, __half* y, int ldy,

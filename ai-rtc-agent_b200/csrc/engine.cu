@@ -99,8 +99,9 @@ class Arena {
 struct Op {
     std::function<int(cudaStream_t)> fn;
     std::string name;
+    double flops = 0.0;  // algorithmic 2*MAC count of the launch (0 for non-contraction kernels)
     template <class F>
-    Op(F f, std::string n = "") : fn(std::move(f)), name(std::move(n)) {}
+    Op(F f, std::string n = "", double fl = 0.0) : fn(std::move(f)), name(std::move(n)), flops(fl) {}
     int operator()(cudaStream_t s) const { return fn(s); }
 };
 
@@ -126,6 +127,7 @@ struct b2sd_engine {
     float* temb_sin = nullptr; // [B][C0]
     float* temb_h = nullptr;   // [B][4*C0]
     float* temb = nullptr;     // [B][4*C0]
+    float* gn_ws = nullptr;    // GroupNorm chunk partials (shared: launches are stream-ordered)
     float* splitk_ws = nullptr;
     size_t splitk_floats = 0;
     float coef_host[4][64]{};
@@ -262,6 +264,7 @@ struct b2sd_engine {
             valid.push_back(bn);
         }
         for (int bn : valid) {
+            if (bn < 64 && n_gemm >= 64) break;  // narrow tiles re-read A too often: prefer split-K below
             d.BN = bn; d.splits = 1; d.partial = nullptr;
             TRY(igemm_plan(d, &plan));
             if ((long)plan.grid.x * plan.grid.y >= 132) { best_bn = bn; break; }
@@ -290,7 +293,8 @@ struct b2sd_engine {
         snprintf(label, sizeof(label), "igemm %s rows=%ld n=%d kb=%d bn=%d splits=%d grid=%u,%u,%u tile=%dx%dx%d", cur.c_str(),
                  plan.rows_total, d.epi.n_valid, plan.p.total_kb, plan.p.BN, plan.splits, plan.grid.x, plan.grid.y,
                  plan.grid.z, plan.p.tn, plan.p.th, plan.p.tw);
-        dst.push_back(Op([plan](cudaStream_t s) { return igemm_launch(plan, s); }, label));
+        dst.push_back(Op([plan](cudaStream_t s) { return igemm_launch(plan, s); }, label,
+                         2.0 * (double)plan.rows_total * n_gemm * plan.p.total_kb * IG_BK));
         return 0;
     }
 
@@ -303,7 +307,8 @@ struct b2sd_engine {
         if (!a.gamma || !a.beta) return -1;
         a.y = y.p; a.ldy = y.ld;
         a.nb = xa.n; a.hw = xa.h * xa.w; a.groups = cfg.norm_groups; a.eps = eps; a.silu = silu;
-        ++launches;
+        a.partial = gn_ws;
+        launches += 2;
         prog_frame.push_back(Op([a](cudaStream_t s) { return groupnorm_launch(a, s); }, "groupnorm " + prefix));
         return 0;
     }
@@ -520,7 +525,8 @@ int b2sd_engine::build_transformer(const std::string& p, const Act& x, int heads
         AttnPlan plan;
         TRY(attn_plan(a, &plan));
         ++launches;
-        prog_frame.push_back(Op([plan](cudaStream_t st) { return attn_launch(plan, st); }, "attn " + p));
+        prog_frame.push_back(Op([plan](cudaStream_t st) { return attn_launch(plan, st); }, "attn " + p,
+                               4.0 * a.nb * a.heads * (double)a.sq * a.skv * a.d_real));
     }
     const Raw* wo1 = get(t + "attn1.to_out.0.weight");
     if (!wo1) return -1;
@@ -560,7 +566,8 @@ int b2sd_engine::build_transformer(const std::string& p, const Act& x, int heads
         AttnPlan plan;
         TRY(attn_plan(a, &plan));
         ++launches;
-        prog_frame.push_back(Op([plan](cudaStream_t st) { return attn_launch(plan, st); }, "attn " + p));
+        prog_frame.push_back(Op([plan](cudaStream_t st) { return attn_launch(plan, st); }, "attn " + p,
+                               4.0 * a.nb * a.heads * (double)a.sq * a.skv * a.d_real));
     }
     const Raw* wo2 = get(t + "attn2.to_out.0.weight");
     if (!wo2) return -1;
@@ -595,7 +602,8 @@ int b2sd_engine::build_transformer(const std::string& p, const Act& x, int heads
         IgemmPlan plan;
         TRY(igemm_plan(d, &plan));
         ++launches;
-        prog_frame.push_back(Op([plan](cudaStream_t st) { return igemm_launch(plan, st); }, "geglu " + p));
+        prog_frame.push_back(Op([plan](cudaStream_t st) { return igemm_launch(plan, st); }, "igemm geglu " + p,
+                               2.0 * (double)M * (2.0 * inner) * C));
     }
     const Raw* wff2 = get(t + "ff.net.2.weight");
     if (!wff2) return -1;
@@ -846,9 +854,10 @@ int b2sd_create(const b2sd_config* cfg, b2sd_handle* out) {
     e->temb_sin = static_cast<float*>(e->state.alloc((size_t)B * C0 * sizeof(float)));
     e->temb_h = static_cast<float*>(e->state.alloc((size_t)B * 4 * C0 * sizeof(float)));
     e->temb = static_cast<float*>(e->state.alloc((size_t)B * 4 * C0 * sizeof(float)));
+    e->gn_ws = static_cast<float*>(e->state.alloc(groupnorm_partial_floats(B, cfg->norm_groups) * sizeof(float)));
     e->splitk_floats = (size_t)24 << 20;  // 96 MB of fp32 partials
     e->splitk_ws = static_cast<float*>(e->state.alloc(e->splitk_floats * sizeof(float)));
-    if (!e->x_in.p || !e->noise || !e->coef || !e->tsteps || !e->ctx || !e->temb || !e->splitk_ws) {
+    if (!e->x_in.p || !e->noise || !e->coef || !e->tsteps || !e->ctx || !e->temb || !e->splitk_ws || !e->gn_ws) {
         b2_set_error("b2sd_create: cudaMalloc failed");
         delete e;
         return -1;
@@ -1040,6 +1049,59 @@ int b2sd_get_tensor(b2sd_handle h, const char* name, void* dst, int64_t capacity
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     CUDA_OK(cudaStreamSynchronize(s));
     CUDA_OK(cudaMemcpy2D(dst, (size_t)a.c * 2, a.p, (size_t)a.ld * 2, (size_t)a.c * 2, (size_t)a.n * a.h * a.w, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// Eager (non-graph) replay with a CUDA event after every launch: per-op device time, averaged over `iters`.
+// Writes a JSON array [{"name": ..., "ms": ...}, ...] into json_buf.  Profiling aid, not the timed path.
+int b2sd_profile(b2sd_handle h, const void* frame_in, int in_h, int in_w, void* frame_out, int iters, char* json_buf,
+                 int64_t cap, void* stream) {
+    if (!h || !h->built || !json_buf || cap < 64) {
+        b2_set_error("b2sd_profile: bad arguments");
+        return -1;
+    }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const size_t nops = h->prog_frame.size() + 2;
+    std::vector<cudaEvent_t> ev(nops + 1);
+    for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
+    std::vector<double> acc(nops, 0.0);
+    SmallConvArgs a = h->head;
+    a.x = frame_in; a.in_h = in_h; a.in_w = in_w; a.flags = SC_IN_U8;
+    for (int it = 0; it < iters + 1; ++it) {  // first iteration is a warm-up
+        CUDA_OK(cudaEventRecord(ev[0], s));
+        TRY(smallconv_launch(a, s));
+        CUDA_OK(cudaEventRecord(ev[1], s));
+        size_t i = 1;
+        for (auto& op : h->prog_frame) {
+            TRY(op(s));
+            ++i;
+            CUDA_OK(cudaEventRecord(ev[i], s));
+        }
+        TRY(post_u8_launch(h->image.p, h->image.ld, static_cast<uint8_t*>(frame_out), 1, h->cfg.height, h->cfg.width, s));
+        CUDA_OK(cudaEventRecord(ev[nops], s));
+        CUDA_OK(cudaStreamSynchronize(s));
+        if (it == 0) continue;
+        for (size_t k = 0; k < nops; ++k) {
+            float ms = 0.f;
+            CUDA_OK(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+            acc[k] += ms;
+        }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    std::string js = "[";
+    char tmp[512];
+    for (size_t k = 0; k < nops; ++k) {
+        const char* nm = k == 0 ? "smallconv head (u8 frame -> 64ch)" : (k == nops - 1 ? "post_u8 tail" : h->prog_frame[k - 1].name.c_str());
+        const double fl = (k == 0 || k == nops - 1) ? 0.0 : h->prog_frame[k - 1].flops;
+        snprintf(tmp, sizeof(tmp), "%s{\"name\": \"%s\", \"ms\": %.6f, \"flops\": %.0f}", k ? ", " : "", nm, acc[k] / iters, fl);
+        js += tmp;
+    }
+    js += "]";
+    if ((int64_t)js.size() + 1 > cap) {
+        b2_set_error("b2sd_profile: buffer too small (%zu needed)", js.size() + 1);
+        return -1;
+    }
+    memcpy(json_buf, js.c_str(), js.size() + 1);
     return 0;
 }
 

@@ -36,19 +36,25 @@ __device__ __forceinline__ void store_half16(__half* dst, const float* v, int nv
         reinterpret_cast<uint4*>(dst)[0] = u[0];
         reinterpret_cast<uint4*>(dst)[1] = u[1];
     } else {
-        for (int i = 0; i < nv; ++i) dst[i] = __float2half_rn(v[i]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (i < nv) dst[i] = __float2half_rn(v[i]);
     }
 }
 
-// 16 accumulator columns [col0, col0+16) of output row `orow` (batch item b).
-__device__ __forceinline__ void epi_store16(const IgEpilogue& e, const float* acc, int b, long orow,
-                                            int col0) {
+// 16 accumulator columns [col0, col0+16) of output row `orow` (batch item b); the accumulators are
+// acc[OFF .. OFF+16) of a register array (compile-time indices only: nothing may spill to local memory).
+template <int OFF, int N, typename T>
+__device__ __forceinline__ void epi_store16(const IgEpilogue& e, const T (&acc)[N], int b, long orow, int col0) {
     int nv = e.n_valid - col0;
     if (nv <= 0) return;
     if (nv > 16) nv = 16;
     float v[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = acc[i];
+    for (int i = 0; i < 16; ++i) {
+        if constexpr (sizeof(T) == 4 && !__is_same(T, float)) v[i] = __uint_as_float(acc[OFF + i]);
+        else v[i] = acc[OFF + i];
+    }
     if (e.colbias) {
         const float* bp = e.colbias + (long)b * e.colbias_bstride + col0;
         if (nv == 16 && (e.colbias_bstride & 3) == 0) {
@@ -58,7 +64,9 @@ __device__ __forceinline__ void epi_store16(const IgEpilogue& e, const float* ac
                 v[4 * i + 0] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
             }
         } else {
-            for (int i = 0; i < nv; ++i) v[i] += bp[i];
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (i < nv) v[i] += bp[i];
         }
     }
     if (e.acc_scale != 1.0f) {
@@ -79,7 +87,9 @@ __device__ __forceinline__ void epi_store16(const IgEpilogue& e, const float* ac
                 v[2 * i + 1] += e.res_scale * f.y;
             }
         } else {
-            for (int i = 0; i < nv; ++i) v[i] += e.res_scale * __half2float(rp[i]);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (i < nv) v[i] += e.res_scale * __half2float(rp[i]);
         }
     }
     if (e.flags & IG_RELU) {
@@ -91,13 +101,13 @@ __device__ __forceinline__ void epi_store16(const IgEpilogue& e, const float* ac
 
 // GEGLU: val/gate are 16 accumulator columns each; packed-column index of val[0] is pcol0 (bias
 // uses packed indexing), output column index is ocol0.
-__device__ __forceinline__ void epi_store16_geglu(const IgEpilogue& e, const float* val,
-                                                  const float* gate, long orow, int pcol_val,
+__device__ __forceinline__ void epi_store16_geglu(const IgEpilogue& e, const uint32_t (&val)[16],
+                                                  const uint32_t (&gate)[16], long orow, int pcol_val,
                                                   int pcol_gate, int ocol0) {
     float v[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        float a = val[i], g = gate[i];
+        float a = __uint_as_float(val[i]), g = __uint_as_float(gate[i]);
         if (e.colbias) {
             a += e.colbias[pcol_val + i];
             g += e.colbias[pcol_gate + i];
@@ -250,9 +260,8 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                 tmem_ld16(taddr + half_n + c, g);
                 tmem_ld_wait();
                 if (row_ok)
-                    epi_store16_geglu(e, reinterpret_cast<const float*>(a),
-                                      reinterpret_cast<const float*>(g), orow, ntile * p.BN + c,
-                                      ntile * p.BN + half_n + c, ntile * half_n + c);
+                    epi_store16_geglu(e, a, g, orow, ntile * p.BN + c, ntile * p.BN + half_n + c,
+                                      ntile * half_n + c);
             }
         } else {
             int c = 0;
@@ -261,16 +270,15 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                 tmem_ld32(taddr + c, v);
                 tmem_ld_wait();
                 if (row_ok) {
-                    epi_store16(e, reinterpret_cast<const float*>(v), n, orow, ntile * p.BN + c);
-                    epi_store16(e, reinterpret_cast<const float*>(v) + 16, n, orow,
-                                ntile * p.BN + c + 16);
+                    epi_store16<0>(e, v, n, orow, ntile * p.BN + c);
+                    epi_store16<16>(e, v, n, orow, ntile * p.BN + c + 16);
                 }
             }
             if (c < p.BN) {
                 uint32_t v[16];
                 tmem_ld16(taddr + c, v);
                 tmem_ld_wait();
-                if (row_ok) epi_store16(e, reinterpret_cast<const float*>(v), n, orow, ntile * p.BN + c);
+                if (row_ok) epi_store16<0>(e, v, n, orow, ntile * p.BN + c);
             }
         }
     }
@@ -300,7 +308,7 @@ __global__ void igemm_finalize_kernel(const float* __restrict__ partial, int spl
             acc[4 * i] += t.x; acc[4 * i + 1] += t.y; acc[4 * i + 2] += t.z; acc[4 * i + 3] += t.w;
         }
     }
-    epi_store16(e, acc, (int)(orow / rows_per_image), orow, col0);
+    epi_store16<0>(e, acc, (int)(orow / rows_per_image), orow, col0);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -261,6 +261,16 @@ class StreamDiffusion:
                                              self._stream()), "b2sd_get_tensor")
         return t
 
+    def profile(self, frame_nhwc: torch.Tensor, iters: int = 5):
+        """Per-launch device times of one frame (eager replay, CUDA events): list of {"name", "ms"}."""
+        import json
+        self._check()
+        out = torch.empty((1, 3, self.height, self.width), dtype=torch.uint8, device=self.device)
+        buf = C.create_string_buffer(1 << 20)
+        capi.check(self._lib.b2sd_profile(self._handle, frame_nhwc.data_ptr(), frame_nhwc.shape[1], frame_nhwc.shape[2],
+                                          out.data_ptr(), iters, buf, len(buf), self._stream()), "b2sd_profile")
+        return json.loads(buf.value.decode())
+
     @property
     def launches_per_step(self) -> int:
         return self._lib.b2sd_launches_per_step(self._handle)

@@ -16,6 +16,15 @@ logger = logging.getLogger(__name__)
 ALLOW_SYNTHETIC_ENV = "B200SD_SYNTHETIC_WEIGHTS"
 
 
+_PRELOADED: Dict[str, tuple] = {}
+
+
+def register_preloaded(model_id: str, arch, unet_sd, vae_sd) -> None:
+    """Make already-materialised weights (e.g. received by NCCL broadcast, host/dist.py) the ones
+    `resolve_weights(model_id, ...)` returns on this process."""
+    _PRELOADED[model_id] = (arch, unet_sd, vae_sd)
+
+
 def find_local_repo(model_id_or_path: str) -> Optional[str]:
     """A directory path, or a HF-cache snapshot of `org/name` under $HF_HUB_CACHE (lib/wrapper.py:437)."""
     if os.path.isdir(model_id_or_path):
@@ -95,6 +104,9 @@ def resolve_weights(model_id_or_path: str, vae_id: Optional[str], lcm_lora_id: O
                     ) -> Tuple[A.UNetArch, Dict[str, torch.Tensor], Dict[str, torch.Tensor], Optional[str]]:
     """Returns (arch, unet_sd, vae_sd, repo_dir or None).  Order: real checkpoint on disk -> synthetic weights if
     $B200SD_SYNTHETIC_WEIGHTS is set (or the id starts with "tiny"/"synthetic") -> error."""
+    if model_id_or_path in _PRELOADED:
+        arch, unet_sd, vae_sd = _PRELOADED[model_id_or_path]
+        return arch, unet_sd, vae_sd, find_local_repo(model_id_or_path)
     arch = A.arch_for(model_id_or_path)
     repo = find_local_repo(model_id_or_path)
     if repo is not None and os.path.isdir(os.path.join(repo, "unet")):

@@ -161,6 +161,10 @@ int b2sd_step_ex(b2sd_handle h, const void* frame_in, int in_kind, int in_h, int
  * Returns the element count via *count (pass dst = NULL to query).  Synchronises `stream`. */
 int b2sd_get_tensor(b2sd_handle h, const char* name, void* dst, int64_t capacity, int64_t* count, int* dims4,
                     void* stream);
+/* Profiling aid: eager replay of one frame with a CUDA event after every launch, averaged over `iters`;
+ * writes a JSON array [{"name","ms"},...] to json_buf.  Synchronises. */
+int b2sd_profile(b2sd_handle h, const void* frame_in, int in_h, int in_w, void* frame_out, int iters,
+                 char* json_buf, int64_t cap, void* stream);
 /* number of kernel launches (graph nodes) in one b2sd_step */
 int b2sd_launches_per_step(b2sd_handle h);
 
