@@ -129,6 +129,7 @@ struct b2sd_engine {
     float* temb = nullptr;     // [B][4*C0]
     float* gn_ws = nullptr;    // GroupNorm chunk partials (shared: launches are stream-ordered)
     float* splitk_ws = nullptr;
+    int* tile_counters = nullptr;
     size_t splitk_floats = 0;
     float coef_host[4][64]{};
 
@@ -276,19 +277,17 @@ struct b2sd_engine {
             d.BN = bn; d.splits = 1; d.partial = nullptr;
             TRY(igemm_plan(d, &plan));
             const long ctas = (long)plan.grid.x * plan.grid.y;
-            int splits = (int)((148 + ctas - 1) / ctas);
+            int splits = ctas >= 96 ? 1 : (int)((148 + ctas - 1) / ctas);
             const int max_by_k = plan.p.total_kb / 4 > 0 ? plan.p.total_kb / 4 : 1;
             if (splits > max_by_k) splits = max_by_k;
-            if (splits > 16) splits = 16;
+            if (splits > 8) splits = 8;
             if (geglu) splits = 1;
-            while (splits > 1 && igemm_partial_floats(splits, plan.rows_total, d.epi.n_valid) > splitk_floats) --splits;
             if (splits > 1) {
                 d.splits = splits;
-                d.partial = splitk_ws;
                 TRY(igemm_plan(d, &plan));
             }
         }
-        launches += 1 + (plan.splits > 1 ? 1 : 0);
+        launches += 1;
         char label[256];
         snprintf(label, sizeof(label), "igemm %s rows=%ld n=%d kb=%d bn=%d splits=%d grid=%u,%u,%u tile=%dx%dx%d", cur.c_str(),
                  plan.rows_total, d.epi.n_valid, plan.p.total_kb, plan.p.BN, plan.splits, plan.grid.x, plan.grid.y,
@@ -857,6 +856,8 @@ int b2sd_create(const b2sd_config* cfg, b2sd_handle* out) {
     e->gn_ws = static_cast<float*>(e->state.alloc(groupnorm_partial_floats(B, cfg->norm_groups) * sizeof(float)));
     e->splitk_floats = (size_t)24 << 20;  // 96 MB of fp32 partials
     e->splitk_ws = static_cast<float*>(e->state.alloc(e->splitk_floats * sizeof(float)));
+    e->tile_counters = static_cast<int*>(e->state.alloc(65536 * sizeof(int)));
+    if (e->tile_counters) cudaMemset(e->tile_counters, 0, 65536 * sizeof(int));
     if (!e->x_in.p || !e->noise || !e->coef || !e->tsteps || !e->ctx || !e->temb || !e->splitk_ws || !e->gn_ws) {
         b2_set_error("b2sd_create: cudaMalloc failed");
         delete e;

@@ -4,6 +4,7 @@
 #include <cudaTypedefs.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ptx.cuh"
@@ -239,18 +240,19 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
         const IgEpilogue& e = p.epi;
         if (e.flags & IG_SPLITK) {
-            float* prow = p.partial + ((long)blockIdx.z * ((long)p.Nb * p.Ho * p.Wo) + orow) * p.n_pad +
-                          ntile * p.BN;
+            // Split-K inside a thread-block cluster (one CTA per K slice, cluster dims (1,1,splits)): every CTA
+            // parks its fp32 partial tile in its own shared memory, laid out [4-column group][row] so that both
+            // these stores and the peers' DSMEM reads are conflict-free; the reduction happens after the cluster
+            // barrier below.
+            float4* stg = reinterpret_cast<float4*>(smem);
             for (int c = 0; c < p.BN; c += 16) {
                 uint32_t v[16];
                 tmem_ld16(taddr + c, v);
                 tmem_ld_wait();
-                if (row_ok) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        reinterpret_cast<uint4*>(prow + c)[i] =
-                            make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                }
+                for (int i = 0; i < 4; ++i)
+                    stg[((c >> 2) + i) * IG_BM + r] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                                  __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
             }
         } else if (e.flags & IG_GEGLU) {
             const int half_n = p.BN / 2;
@@ -282,33 +284,42 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
             }
         }
     }
+    if (p.epi.flags & IG_SPLITK) {
+        // ---- cluster-wide deterministic reduction over the K slices through distributed shared memory ----
+        const int splits = (int)gridDim.z;
+        cluster_sync_all();  // all partial tiles are in place (release/acquire over the cluster)
+        if (warp >= 2) {
+            const int rank = (int)cluster_ctarank();
+            const int rows_per = IG_BM / splits;          // splits in {2,4,8}
+            const int t = threadIdx.x - 64;               // 0..127
+            const int chunks = p.BN >> 4;
+            const uint32_t stg_local = smem_u32(smem);
+            for (int item = t; item < rows_per * chunks; item += 128) {
+                const int rl = item % rows_per;
+                const int cc = item / rows_per;
+                const int r = rank * rows_per + rl;       // row of the tile this CTA finalises
+                const int wi = r % p.tw, hi = (r / p.tw) % p.th, ni = r / (p.tw * p.th);
+                const int n = n0 + ni, h = h0 + hi, w = w0 + wi;
+                const bool ok = (ni < p.tn) && (n < p.Nb) && (h < p.Ho) && (w < p.Wo);
+                float acc[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+                for (int sidx = 0; sidx < splits; ++sidx) {   // fixed order => bit-reproducible
+                    const uint32_t peer = dsmem_map(stg_local, (uint32_t)sidx);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 v = dsmem_ld_f4(peer + (uint32_t)(((cc * 4 + i) * IG_BM + r) * 16));
+                        acc[4 * i] += v.x; acc[4 * i + 1] += v.y; acc[4 * i + 2] += v.z; acc[4 * i + 3] += v.w;
+                    }
+                }
+                if (ok) epi_store16<0>(p.epi, acc, n, ((long)n * p.Ho + h) * p.Wo + w, ntile * p.BN + cc * 16);
+            }
+        }
+        cluster_sync_all();  // nobody may exit while a peer still reads its shared memory
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
-}
-
-// sum split-K partials and apply the epilogue; one thread = 16 columns of one output row
-__global__ void igemm_finalize_kernel(const float* __restrict__ partial, int splits, long rows_total,
-                                      int n_pad, int rows_per_image, IgEpilogue e) {
-    const int chunks = n_pad / 16;
-    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= rows_total * chunks) return;
-    const long orow = idx / chunks;
-    const int col0 = (int)(idx % chunks) * 16;
-    if (col0 >= e.n_valid) return;
-    float acc[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-    for (int s = 0; s < splits; ++s) {
-        const float4* pp =
-            reinterpret_cast<const float4*>(partial + ((long)s * rows_total + orow) * n_pad + col0);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float4 t = pp[i];
-            acc[4 * i] += t.x; acc[4 * i + 1] += t.y; acc[4 * i + 2] += t.z; acc[4 * i + 3] += t.w;
-        }
-    }
-    epi_store16<0>(e, acc, (int)(orow / rows_per_image), orow, col0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -462,18 +473,23 @@ int igemm_plan(const IgemmDesc& d, IgemmPlan* plan) {
     // ---- split-K
     int splits = d.splits < 1 ? 1 : d.splits;
     if (splits > total_kb) splits = total_kb;
+    if (splits >= 8) splits = 8;        // portable cluster size; power of two so rows divide evenly
+    else if (splits >= 4) splits = 4;
+    else if (splits >= 2) splits = 2;
     p.kb_per_split = (total_kb + splits - 1) / splits;
-    splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+    while (splits > 1 && (total_kb + p.kb_per_split - 1) / p.kb_per_split != splits) {  // keep every slice non-empty
+        splits >>= 1;
+        p.kb_per_split = (total_kb + splits - 1) / splits;
+    }
     plan->splits = splits;
     plan->rows_total = (long)d.Nb * d.Ho * d.Wo;
     p.epi = d.epi;
     p.n_pad = n_tiles * BN;
     if (splits > 1) {
-        if (geglu || !d.partial) {
-            b2_set_error("igemm: split-K needs a workspace and no GEGLU");
+        if (geglu) {
+            b2_set_error("igemm: split-K cannot be combined with GEGLU");
             return -1;
         }
-        p.partial = d.partial;
         p.epi.flags |= IG_SPLITK;
     }
     // ---- pipeline depth / smem
@@ -483,7 +499,22 @@ int igemm_plan(const IgemmDesc& d, IgemmPlan* plan) {
     if (stages > IG_MAX_STAGES) stages = IG_MAX_STAGES;
     if (stages > p.kb_per_split) stages = p.kb_per_split < 2 ? 2 : p.kb_per_split;
     p.num_stages = stages;
-    plan->smem = stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    size_t pipe_bytes = stages * stage_bytes;
+    if (splits > 1) {
+        // the split-K staging tile [BN/4][128] float4 reuses the pipeline buffers
+        const size_t stg = (size_t)BN * IG_BM * 4;
+        if (stg > pipe_bytes) {
+            // grow the ring rather than carving a second region (barriers live right after the ring)
+            stages = (int)((stg + stage_bytes - 1) / stage_bytes);
+            if (stages > IG_MAX_STAGES) {
+                b2_set_error("igemm: split-K staging does not fit (BN %d)", BN);
+                return -1;
+            }
+            p.num_stages = stages;
+            pipe_bytes = stages * stage_bytes;
+        }
+    }
+    plan->smem = pipe_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
     uint32_t cols = 32;
     while (cols < (uint32_t)BN) cols <<= 1;
     p.tmem_cols = cols;
@@ -508,24 +539,25 @@ int igemm_init() {
 
 int igemm_launch(const IgemmPlan& plan, cudaStream_t stream) {
     if (igemm_init()) return -1;
-    igemm_kernel<<<plan.grid, IG_THREADS, plan.smem, stream>>>(plan.p);
-    cudaError_t e = cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = plan.grid;
+    cfg.blockDim = dim3(IG_THREADS);
+    cfg.dynamicSmemBytes = plan.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    if (plan.splits > 1) {
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = (unsigned)plan.splits;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_kernel, plan.p);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
         b2_set_error("igemm launch: %s", cudaGetErrorString(e));
         return -1;
-    }
-    if (plan.splits > 1) {
-        IgEpilogue epi = plan.p.epi;
-        epi.flags &= ~IG_SPLITK;
-        const long total = plan.rows_total * (plan.p.n_pad / 16);
-        const int threads = 256;
-        igemm_finalize_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(
-            plan.p.partial, plan.splits, plan.rows_total, plan.p.n_pad, plan.p.Ho * plan.p.Wo, epi);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) {
-            b2_set_error("igemm finalize launch: %s", cudaGetErrorString(e));
-            return -1;
-        }
     }
     return 0;
 }

@@ -58,6 +58,7 @@ struct IgemmParams {
     uint32_t b_bytes;
     uint32_t tmem_cols;
     float* partial;               // [splits][rows_total][n_pad] fp32 (split-K only)
+    int* tile_counters;           // one int per (m tile, n tile), zero between launches (split-K only)
     int n_pad;
     IgEpilogue epi;
 };
@@ -80,6 +81,7 @@ struct IgemmDesc {
     int BN;           // 0 = auto
     int splits;       // 0/1 = none
     float* partial;   // workspace for split-K (size splits*rows*n_pad floats)
+    int* tile_counters;  // >= m_tiles*n_tiles zero-initialised ints (self re-arming)
     IgEpilogue epi;
 };
 

@@ -10,6 +10,9 @@ import torch
 from . import capi
 
 
+_SCRATCH = {}  # split-K workspaces kept alive between calls (stream-ordered reuse)
+
+
 def pack_conv_weight(w_oihw: torch.Tensor) -> torch.Tensor:
     """[O,I,kh,kw] -> [O, kh*kw*I] fp16 with K order [tap][c] (tap = ky*kw + kx)."""
     o, i, kh, kw = w_oihw.shape
@@ -44,11 +47,11 @@ def igemm(srcs: Sequence[Tuple[torch.Tensor, int]], w: torch.Tensor, out: torch.
     d.out, d.ldc = out.data_ptr(), out.stride(2)
     nv = n_valid if n_valid is not None else out.shape[3]
     d.n_valid = nv
-    keep = []
     if splits > 1:
         nfl = capi.lib().b2sd_igemm_partial_floats(splits, nb * ho * wo, nv)
-        part = torch.empty(nfl, dtype=torch.float32, device=out.device)
-        keep.append(part)
+        part = _SCRATCH.get((nfl, out.device))
+        if part is None:
+            part = _SCRATCH[(nfl, out.device)] = torch.empty(nfl, dtype=torch.float32, device=out.device)
         d.partial = part.data_ptr()
     if colbias is not None:
         assert colbias.dtype == torch.float32 and colbias.is_contiguous()
@@ -60,8 +63,6 @@ def igemm(srcs: Sequence[Tuple[torch.Tensor, int]], w: torch.Tensor, out: torch.
     d.acc_scale, d.res_scale = acc_scale, res_scale
     d.flags = (capi.IG_RELU if relu else 0) | (capi.IG_GEGLU if geglu else 0)
     capi.check(capi.lib().b2sd_op_igemm(C.byref(d), capi.current_stream_ptr()), "b2sd_op_igemm")
-    if keep:
-        torch.cuda.current_stream().synchronize()
     return out
 
 

@@ -1,0 +1,186 @@
+"""CPU tests of the host side (no GPU): C-ABI surface, reference-shaped argument validation, schedule tables,
+weight plumbing, frame-type handling, and the multi-process weight broadcast over gloo."""
+import ctypes
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shared_library_exports_every_declared_symbol():
+    from ai_rtc_agent_b200.host import capi
+    lib = capi.lib()
+    header = open(os.path.join(ROOT, "include", "b200sd.h")).read()
+    names = sorted(set(re.findall(r"\b(b2sd_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/b200sd.h but not exported by libb200sd.so"
+    assert lib.b2sd_version() >= 1
+    assert isinstance(lib.b2sd_last_error(), (bytes, type(None)))
+
+
+def test_ctypes_struct_layout_matches_the_c_header(tmp_path):
+    """Compile include/b200sd.h with gcc (plain C: the header must stay C-clean) and compare sizeof()."""
+    import subprocess
+    from ai_rtc_agent_b200.host import capi
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "b200sd.h"\nint main(void){printf("%zu %zu %zu %zu\\n", sizeof(b2sd_act_view), '
+                   'sizeof(b2sd_igemm_desc), sizeof(b2sd_attn_desc), sizeof(b2sd_config)); return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    sizes = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [ctypes.sizeof(capi.ActView), ctypes.sizeof(capi.IgemmDesc), ctypes.sizeof(capi.AttnDesc),
+                     ctypes.sizeof(capi.EngineConfig)]
+
+
+def test_no_cpu_fallback():
+    """Without a GPU the product path must fail loudly, not fall back to the oracle."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from ai_rtc_agent_b200.host import capi
+    from ai_rtc_agent_b200.host.wrapper import StreamDiffusionWrapper
+    with pytest.raises(capi.B2Error):
+        StreamDiffusionWrapper("tiny-turbo", [10])
+    src = ""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "ai-rtc-agent_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src += open(os.path.join(dirpath, f)).read()
+    for mod in ("lib/pipeline.py", "lib/wrapper.py"):
+        src += open(os.path.join(ROOT, mod)).read()
+    assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), "product code must never import the oracle"
+
+
+def test_wrapper_validation_matches_reference_errors():
+    from ai_rtc_agent_b200.host.wrapper import StreamDiffusionWrapper
+    with pytest.raises(ValueError, match="txt2img mode accepts only cfg_type = 'none'"):   # lib/wrapper.py:135-139
+        StreamDiffusionWrapper("m", [1], mode="txt2img")
+    with pytest.raises(ValueError, match="frame_buffer_size > 1"):                          # lib/wrapper.py:140-144
+        StreamDiffusionWrapper("m", [1], mode="txt2img", cfg_type="none", frame_buffer_size=2)
+    with pytest.raises(NotImplementedError, match="img2img mode must use denoising batch"):  # lib/wrapper.py:146-150
+        StreamDiffusionWrapper("m", [1], use_denoising_batch=False)
+    with pytest.raises(NotImplementedError):
+        StreamDiffusionWrapper("m", [1], use_safety_checker=True)
+    with pytest.raises(FileNotFoundError):
+        os.environ.pop("B200SD_SYNTHETIC_WEIGHTS", None)
+        StreamDiffusionWrapper("no/such-model", [1])
+
+
+def test_reference_import_surface():
+    sys.path.insert(0, ROOT)
+    import lib.pipeline as P
+    import lib.wrapper as Wm
+    assert P.DEFAULT_PROMPT == "fireworks in the night sky" and P.DEFAULT_T_INDEX_LIST == [18, 26, 35, 45]
+    assert P.DEFAULT_NUM_INFERENCE_STEPS == 50 and P.DEFAULT_GUIDANCE_SCALE == 0.0
+    for m in ("update_prompt", "update_t_index_list", "preprocess", "predict", "postprocess", "__call__"):
+        assert callable(getattr(P.StreamDiffusionPipeline, m))
+    for m in ("prepare", "img2img", "txt2img", "preprocess_image", "postprocess_image", "update_t_index_list", "__call__"):
+        assert callable(getattr(Wm.StreamDiffusionWrapper, m))
+    import inspect
+    sig = inspect.signature(Wm.StreamDiffusionWrapper.__init__)
+    ref_kwargs = ["model_id_or_path", "t_index_list", "controlnet_id_or_path", "controlnet_processor_id", "lora_dict", "mode",
+                  "output_type", "lcm_lora_id", "vae_id", "device", "dtype", "frame_buffer_size", "width", "height", "warmup",
+                  "acceleration", "do_add_noise", "device_ids", "use_lcm_lora", "use_tiny_vae", "enable_similar_image_filter",
+                  "similar_image_filter_threshold", "similar_image_filter_max_skip_frame", "use_denoising_batch", "cfg_type",
+                  "seed", "use_safety_checker", "engine_dir", "cuda_stream_handle"]
+    assert list(sig.parameters)[1:] == ref_kwargs                       # lib/wrapper.py:35-66, same order
+    d = {k: v.default for k, v in sig.parameters.items()}
+    assert d["width"] == 512 and d["height"] == 512 and d["acceleration"] == "tensorrt" and d["cfg_type"] == "self"
+    assert d["seed"] == 2 and d["engine_dir"] == "engines" and d["output_type"] == "pil" and d["warmup"] == 10
+    assert Wm.CudaStreamPtr(1234).ptr == 1234
+
+
+def test_invalid_frame_type_raises_like_reference():
+    from ai_rtc_agent_b200.host.pipeline import StreamDiffusionPipeline
+    p = StreamDiffusionPipeline.__new__(StreamDiffusionPipeline)
+    p.device = "cuda"
+    with pytest.raises(Exception, match="invalid frame type"):          # lib/pipeline.py:51-52
+        p.preprocess("not a frame")
+    with pytest.raises(Exception, match="invalid frame type"):
+        p(torch.zeros(1, 8, 8, 3, dtype=torch.uint8))                   # CPU tensor is neither NVDEC nor av frame
+
+
+def test_schedule_tables_agree_with_oracle():
+    from ai_rtc_agent_b200.host import stream as hs
+    from oracle import stream as ostream
+    assert hs.lcm_timestep_table(50) == ostream.lcm_timesteps(50)
+    assert hs.lcm_timestep_table(10) == ostream.lcm_timesteps(10)
+    assert torch.equal(hs.scaled_linear_alphas_cumprod(), ostream.alphas_cumprod())
+    for t in (99, 299, 479, 639, 999):
+        a, b = hs.lcm_boundary_scalings(t), ostream.boundary_scalings(t)
+        assert abs(a[0] - b[0]) < 1e-12 and abs(a[1] - b[1]) < 1e-12
+
+
+def test_two_independent_parameter_inventories_agree():
+    """host/arch.py and oracle/unet.py enumerate the checkpoint layout independently."""
+    from ai_rtc_agent_b200.host import arch as A
+    from oracle import taesd as otaesd
+    from oracle import unet as ounet
+    assert A.unet_param_shapes(A.SD15) == ounet.param_shapes(ounet.SD15)
+    assert A.unet_param_shapes(A.SD_TURBO) == ounet.param_shapes(ounet.SD_TURBO)
+    assert A.unet_param_shapes(A.TINY_TURBO) == ounet.param_shapes(ounet.tiny_config(True))
+    assert A.unet_param_shapes(A.TINY_SD15) == ounet.param_shapes(ounet.tiny_config(False))
+    assert A.taesd_param_shapes() == otaesd.param_shapes()
+    assert A.arch_for("stabilityai/sd-turbo") is A.SD_TURBO and A.arch_for("lykon/dreamshaper-8") is A.SD15
+
+
+def test_fuse_lora_math():
+    from ai_rtc_agent_b200.host.weights import fuse_lora
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(8, 6, generator=g).half()
+    down, up = torch.randn(2, 6, generator=g), torch.randn(8, 2, generator=g)
+    sd = {"down_blocks.0.attentions.0.transformer_blocks.0.attn1.to_q.weight": w.clone()}
+    lora = {"unet.down_blocks.0.attentions.0.transformer_blocks.0.attn1.to_q.lora_A.weight": down,
+            "unet.down_blocks.0.attentions.0.transformer_blocks.0.attn1.to_q.lora_B.weight": up,
+            "unet.down_blocks.0.attentions.0.transformer_blocks.0.attn1.to_q.alpha": torch.tensor(4.0)}
+    assert fuse_lora(sd, lora, scale=0.5) == 1
+    ref = (w.float() + 0.5 * (4.0 / 2) * (up @ down)).half()
+    assert torch.equal(list(sd.values())[0], ref)
+
+
+def test_synthetic_weights_are_seeded_and_scaled():
+    from ai_rtc_agent_b200.host import arch as A
+    s1 = A.synthetic_state_dict(A.unet_param_shapes(A.TINY_TURBO), seed=7)
+    s2 = A.synthetic_state_dict(A.unet_param_shapes(A.TINY_TURBO), seed=7)
+    assert all(torch.equal(s1[k], s2[k]) for k in s1)
+    w = s1["down_blocks.0.resnets.0.conv1.weight"].float()
+    assert abs(w.std().item() * (w[0].numel() ** 0.5) - 1.0) < 0.1
+    A.validate_state_dict(s1, A.unet_param_shapes(A.TINY_TURBO), "tiny")
+    with pytest.raises(ValueError):
+        A.validate_state_dict({}, A.unet_param_shapes(A.TINY_TURBO), "empty")
+
+
+def _bcast_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from ai_rtc_agent_b200.host import arch as A
+    from ai_rtc_agent_b200.host import dist as bd
+    bd.init(backend="gloo")
+    shapes = A.taesd_param_shapes()
+    sd = A.synthetic_state_dict(shapes, seed=11, relu_net=True) if rank == 0 else None
+    out = bd.broadcast_state_dict(sd, shapes, torch.device("cpu"))
+    digest = sum(float(v.float().abs().sum()) for v in out.values())
+    q.put((rank, digest, len(out)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_weight_broadcast_world_size_2_gloo():
+    """N>1 path on CPU: rank 0 owns the weights, every rank ends with identical copies, one broadcast."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_bcast_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == res[1][1] and res[0][2] == res[1][2] > 50
