@@ -90,6 +90,14 @@ int b2sd_op_groupnorm(const void* xa, int ca, int lda, const void* xb, int cb, i
         scratch_floats = need;
     }
     a.partial = scratch;
+    static int* gn_counters = nullptr;
+    if (!gn_counters) {
+        if (cudaMalloc(&gn_counters, 64 * sizeof(int)) != cudaSuccess || cudaMemset(gn_counters, 0, 64 * sizeof(int)) != cudaSuccess) {
+            b2_set_error("b2sd_op_groupnorm: counter alloc failed");
+            return -1;
+        }
+    }
+    a.counters = gn_counters;
     return groupnorm_launch(a, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -107,7 +115,14 @@ int b2sd_op_upsample2x(const void* x, void* y, int nb, int h, int w, int c, void
 int b2sd_op_smallconv(const void* x, const void* w_oihw, const float* bias, void* y, int ldy, int nb, int h,
                       int w, int cin, int cout, int in_h, int in_w, int flags, void* stream) {
     SmallConvArgs a{};
-    a.x = x; a.w = reinterpret_cast<const __half*>(w_oihw); a.bias = bias;
+    static float* wt = nullptr;  // op-level entry only: re-prepared on every call
+    if (!wt && cudaMalloc(&wt, 36 * 1024 * sizeof(float)) != cudaSuccess) {
+        b2_set_error("b2sd_op_smallconv: cudaMalloc failed");
+        return -1;
+    }
+    if (cout > 1024 || smallconv_prep_launch(reinterpret_cast<const __half*>(w_oihw), wt, cout, cin, reinterpret_cast<cudaStream_t>(stream)))
+        return -1;
+    a.x = x; a.wt = wt; a.bias = bias;
     a.y = reinterpret_cast<__half*>(y); a.ldy = ldy;
     a.nb = nb; a.h = h; a.w_ = w; a.cin = cin; a.cout = cout; a.in_h = in_h; a.in_w = in_w; a.flags = flags;
     return smallconv_launch(a, reinterpret_cast<cudaStream_t>(stream));

@@ -1,6 +1,8 @@
 // SIMT helper kernels: normalisation, resampling, tiny convolutions, scheduler step, pre/post.
 #include "elementwise.cuh"
 
+#include <stdio.h>
+
 #include "igemm.cuh"  // b2_set_error
 
 namespace b2 {
@@ -15,6 +17,11 @@ namespace b2 {
     } while (0)
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ uint64_t globaltimer_ns_ew() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 template <typename T>
 __device__ __forceinline__ T block_reduce_sum(T v, T* scratch) {
@@ -90,25 +97,47 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(GroupNormArgs a, int ppc,
     }
 }
 
+// mean / rstd of every group of batch item b from the per-chunk partial sums, computed by the whole CTA in a
+// fixed order (thread (slice, g) sums chunks slice, slice+S, ...; then thread g sums the S slices).
+__device__ __forceinline__ void gn_finalize_stats(const GroupNormArgs& a, int b, int nchunks, float* scratch /*[S][G][2]*/,
+                                                  float* s_mean, float* s_rstd) {
+    const int G = a.groups;
+    const int S = min(16, (int)blockDim.x / G);
+    const int g = threadIdx.x % G, slice = threadIdx.x / G;
+    if (slice < S) {
+        float gs = 0.f, gq = 0.f;
+        const float* src = a.partial + ((long)b * GN_MAX_CHUNKS * G + g) * 2;
+        for (int k = slice; k < nchunks; k += S) {
+            const float2 v = __ldcg(reinterpret_cast<const float2*>(src + (long)k * G * 2));
+            gs += v.x;
+            gq += v.y;
+        }
+        scratch[(slice * G + g) * 2] = gs;
+        scratch[(slice * G + g) * 2 + 1] = gq;
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+        float gs = 0.f, gq = 0.f;
+        for (int k = 0; k < S; ++k) {
+            gs += scratch[(k * G + threadIdx.x) * 2];
+            gq += scratch[(k * G + threadIdx.x) * 2 + 1];
+        }
+        const int cpg = (a.ca + a.cb) / G;
+        const float inv_n = 1.0f / ((float)a.hw * (float)cpg);
+        const float mean = gs * inv_n;
+        s_mean[threadIdx.x] = mean;
+        s_rstd[threadIdx.x] = rsqrtf(fmaxf(gq * inv_n - mean * mean, 0.f) + a.eps);
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(256) gn_apply_kernel(GroupNormArgs a, int nchunks, long vec_per_batch) {
     __shared__ float s_mean[64], s_rstd[64];
+    __shared__ float s_scratch[16 * 64 * 2];
     const int C = a.ca + a.cb;
     const int b = blockIdx.y;
     const int cpg = C / a.groups;
-    if (threadIdx.x < a.groups) {
-        float gs = 0.f, gq = 0.f;
-        const float* src = a.partial + ((long)b * GN_MAX_CHUNKS * a.groups + threadIdx.x) * 2;
-        for (int k = 0; k < nchunks; ++k) {
-            gs += src[(long)k * a.groups * 2];
-            gq += src[(long)k * a.groups * 2 + 1];
-        }
-        const float inv_n = 1.0f / ((float)a.hw * (float)cpg);
-        const float mean = gs * inv_n;
-        const float var = fmaxf(gq * inv_n - mean * mean, 0.f);
-        s_mean[threadIdx.x] = mean;
-        s_rstd[threadIdx.x] = rsqrtf(var + a.eps);
-    }
-    __syncthreads();
+    gn_finalize_stats(a, b, nchunks, s_scratch, s_mean, s_rstd);
     const int vc = C / 8;
     for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < vec_per_batch; e += (long)gridDim.x * blockDim.x) {
         const int col = (int)(e % vc);
@@ -149,7 +178,127 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GroupNormArgs a, int nchu
     }
 }
 
-size_t groupnorm_partial_floats(int nb, int groups) { return (size_t)nb * GN_MAX_CHUNKS * groups * 2; }
+// Single-launch variant: statistics, a per-batch-item grid barrier (cooperative launch guarantees co-residency),
+// then normalise straight from the registers that still hold the chunk.  counters: 2 ints per batch item, zero
+// between launches (the last CTA to leave re-arms them).
+constexpr int GN_CACHE = 12;
+__global__ void __launch_bounds__(512) gn_fused_kernel(GroupNormArgs a, int ppc, int vc, int rpi, int* counters) {
+    extern __shared__ float sm[];
+    __shared__ float s_mean[64], s_rstd[64];
+    const int C = a.ca + a.cb;
+    const int chunk = blockIdx.x, b = blockIdx.y, nchunks = gridDim.x;
+    const int col = threadIdx.x % vc, prow = threadIdx.x / vc;
+    const int c0 = col * 8;
+    const bool from_a = c0 < a.ca;
+    const __half* base = from_a ? a.xa + c0 : a.xb + (c0 - a.ca);
+    const int ld = from_a ? a.lda : a.ldb;
+    const int p_begin = chunk * ppc, p_end = min(a.hw, p_begin + ppc);
+    uint4 cache[GN_CACHE];
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+    if (prow < rpi) {
+#pragma unroll
+        for (int it = 0; it < GN_CACHE; ++it) {
+            const int p = p_begin + prow + it * rpi;
+            if (p < p_end) {
+                const uint4 u = *reinterpret_cast<const uint4*>(base + ((long)b * a.hw + p) * ld);
+                cache[it] = u;
+                const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __half22float2(h[i]);
+                    s[2 * i] += f.x; q[2 * i] += f.x * f.x;
+                    s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            sm[((long)prow * C + c0 + i) * 2] = s[i];
+            sm[((long)prow * C + c0 + i) * 2 + 1] = q[i];
+        }
+    }
+    __syncthreads();
+    const int cpg = C / a.groups;
+    for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
+        float gs = 0.f, gq = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c)
+            for (int r = 0; r < rpi; ++r) {
+                gs += sm[((long)r * C + c) * 2];
+                gq += sm[((long)r * C + c) * 2 + 1];
+            }
+        float* dst = a.partial + (((long)b * GN_MAX_CHUNKS + chunk) * a.groups + g) * 2;
+        dst[0] = gs;
+        dst[1] = gq;
+    }
+    // ---- barrier over the CTAs of this batch item
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int* cnt = counters + 2 * b;
+        atomicAdd(cnt, 1);
+        const uint64_t t0 = globaltimer_ns_ew();
+        while (true) {
+            int seen;
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
+            if (seen >= nchunks) break;
+            __nanosleep(32);
+            if (globaltimer_ns_ew() - t0 > 4000000000ull) {
+                printf("b2: groupnorm grid barrier timeout\n");
+                __trap();
+            }
+        }
+        if (atomicAdd(cnt + 1, 1) == nchunks - 1) {  // last one out re-arms both counters for the next launch
+            cnt[1] = 0;
+            __threadfence();
+            cnt[0] = 0;
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    gn_finalize_stats(a, b, nchunks, sm, s_mean, s_rstd);  // sm (>= 16*G*2 floats) is free again
+    if (prow < rpi) {
+        const float4 g0 = *reinterpret_cast<const float4*>(a.gamma + c0);
+        const float4 g1 = *reinterpret_cast<const float4*>(a.gamma + c0 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(a.beta + c0);
+        const float4 b1 = *reinterpret_cast<const float4*>(a.beta + c0 + 4);
+        const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bet[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float mu[8], rs[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int g = (c0 + i) / cpg;
+            mu[i] = s_mean[g];
+            rs[i] = s_rstd[g] * gam[i];
+        }
+#pragma unroll
+        for (int it = 0; it < GN_CACHE; ++it) {
+            const int p = p_begin + prow + it * rpi;
+            if (p < p_end) {
+                const __half2* h = reinterpret_cast<const __half2*>(&cache[it]);
+                uint4 o;
+                __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __half22float2(h[i]);
+                    float y0 = (f.x - mu[2 * i]) * rs[2 * i] + bet[2 * i];
+                    float y1 = (f.y - mu[2 * i + 1]) * rs[2 * i + 1] + bet[2 * i + 1];
+                    if (a.silu) {
+                        y0 = silu_f(y0);
+                        y1 = silu_f(y1);
+                    }
+                    oh[i] = __floats2half2_rn(y0, y1);
+                }
+                *reinterpret_cast<uint4*>(a.y + ((long)b * a.hw + p) * a.ldy + c0) = o;
+            }
+        }
+    }
+}
+
+static thread_local int g_gn_last_launches = 0;
+int groupnorm_last_launch_count() { return g_gn_last_launches; }
+size_t groupnorm_partial_floats(int nb, int groups) { return (size_t)nb * GN_MAX_CHUNKS * groups * 2 + 64; }
 
 int groupnorm_launch(const GroupNormArgs& a, cudaStream_t s) {
     const int C = a.ca + a.cb;
@@ -171,11 +320,38 @@ int groupnorm_launch(const GroupNormArgs& a, cudaStream_t s) {
     if (rpi > ppc) rpi = ppc;
     const int nchunks = (a.hw + ppc - 1) / ppc;
     const int threads = ((vc * rpi + 31) / 32) * 32;
-    const size_t smem = (size_t)rpi * C * 2 * sizeof(float);
+    size_t smem = (size_t)rpi * C * 2 * sizeof(float);
+    if (smem < 16 * 64 * 2 * sizeof(float)) smem = 16 * 64 * 2 * sizeof(float);  // also the stats-finalise scratch
     static bool attr = false;
+    static int max_coop_blocks_per_sm = 0;
     if (!attr) {
         cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         attr = true;
+    }
+    // single cooperative launch when the whole grid is co-resident and a chunk fits the register cache
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel, threads, smem);
+    (void)max_coop_blocks_per_sm;
+    const bool fits = (ppc + rpi - 1) / rpi <= GN_CACHE && (long)nchunks * a.nb <= (long)per_sm * 148 && a.nb <= 16;
+    if (fits && a.counters) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(nchunks, a.nb);
+        cfg.blockDim = dim3(threads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeCooperative;
+        at[0].val.cooperative = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, gn_fused_kernel, a, ppc, vc, rpi, a.counters);
+        if (e != cudaSuccess) {
+            b2_set_error("gn_fused launch: %s", cudaGetErrorString(e));
+            return -1;
+        }
+        g_gn_last_launches = 1;
+        return 0;
     }
     gn_stats_kernel<<<dim3(nchunks, a.nb), threads, smem, s>>>(a, ppc, vc, rpi);
     B2_CHECK_LAUNCH("gn_stats");
@@ -185,6 +361,7 @@ int groupnorm_launch(const GroupNormArgs& a, cudaStream_t s) {
     if (blocks > cap) blocks = cap;
     gn_apply_kernel<<<dim3((unsigned)blocks, a.nb), 256, 0, s>>>(a, nchunks, vec_per_batch);
     B2_CHECK_LAUNCH("gn_apply");
+    g_gn_last_launches = 2;
     return 0;
 }
 
@@ -274,25 +451,41 @@ int upsample2x_launch(const __half* x, __half* y, int nb, int h, int w, int c, c
 }
 
 // ------------------------------------------------------------------------------------------ small conv
-// thread = (pixel, 8 output channels); weights staged in smem as fp32 [k][cout]
+// thread = (pixel, 64 output channels): the 3x3xCIN patch lives in registers, the fp32 weights [k][cout]
+// (k = tap*CIN + c, prepared once by smallconv_prep_launch) in shared memory where a warp reads them as broadcasts.
+__global__ void smallconv_prep_kernel(const __half* __restrict__ w_oihw, float* __restrict__ wt, int cout, int cin) {
+    const int K = cin * 9;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K * cout; i += gridDim.x * blockDim.x) {
+        const int o = i % cout, k = i / cout;
+        const int tap = k / cin, c = k % cin;
+        wt[i] = __half2float(w_oihw[((long)o * cin + c) * 9 + tap]);
+    }
+}
+int smallconv_prep_launch(const __half* w_oihw, float* wt, int cout, int cin, cudaStream_t s) {
+    smallconv_prep_kernel<<<(cin * 9 * cout + 255) / 256, 256, 0, s>>>(w_oihw, wt, cout, cin);
+    B2_CHECK_LAUNCH("smallconv_prep");
+    return 0;
+}
+
 template <int CIN>
-__global__ void __launch_bounds__(256) smallconv_kernel(SmallConvArgs a) {
+__global__ void __launch_bounds__(128) smallconv_kernel(SmallConvArgs a) {
     extern __shared__ float ws[];  // [CIN*9][cout] then bias[cout]
     constexpr int K = CIN * 9;
     const int cout = a.cout;
-    for (int i = threadIdx.x; i < K * cout; i += blockDim.x) {
-        const int o = i % cout, k = i / cout;  // k = tap*CIN + c
-        const int tap = k / CIN, c = k % CIN;
-        ws[i] = __half2float(a.w[((long)o * CIN + c) * 9 + tap]);
+    {
+        const float4* src = reinterpret_cast<const float4*>(a.wt);
+        float4* dst = reinterpret_cast<float4*>(ws);
+        for (int i = threadIdx.x; i < K * cout / 4; i += blockDim.x) dst[i] = src[i];
     }
     float* bs = ws + K * cout;
     for (int i = threadIdx.x; i < cout; i += blockDim.x) bs[i] = a.bias ? a.bias[i] : 0.f;
     __syncthreads();
-    const int groups = cout >> 3;
-    const long total = (long)a.nb * a.h * a.w_ * groups;
+    const int groups = cout >> 6;
+    const long npix = (long)a.nb * a.h * a.w_;
+    const long total = npix * groups;
     for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-        const int cg = (int)(e % groups);
-        long p = e / groups;
+        const int cg = (int)(e / npix);  // consecutive threads = consecutive pixels of the same channel group
+        const long p = e % npix;
         const int xw = (int)(p % a.w_);
         const int yh = (int)((p / a.w_) % a.h);
         const int n = (int)(p / ((long)a.w_ * a.h));
@@ -328,48 +521,56 @@ __global__ void __launch_bounds__(256) smallconv_kernel(SmallConvArgs a) {
                 patch[tap * CIN + c] = v;
             }
         }
-        float acc[8];
+        float acc[64];
+        const float* bsg = bs + cg * 64;
 #pragma unroll
-        for (int o = 0; o < 8; ++o) acc[o] = bs[cg * 8 + o];
+        for (int o = 0; o < 64; ++o) acc[o] = bsg[o];
+        const float* wg = ws + cg * 64;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const float4 w0 = *reinterpret_cast<const float4*>(&ws[k * cout + cg * 8]);
-            const float4 w1 = *reinterpret_cast<const float4*>(&ws[k * cout + cg * 8 + 4]);
             const float v = patch[k];
-            acc[0] += v * w0.x; acc[1] += v * w0.y; acc[2] += v * w0.z; acc[3] += v * w0.w;
-            acc[4] += v * w1.x; acc[5] += v * w1.y; acc[6] += v * w1.z; acc[7] += v * w1.w;
-        }
-        uint4 u;
-        __half2* hh = reinterpret_cast<__half2*>(&u);
 #pragma unroll
-        for (int o = 0; o < 4; ++o) {
-            float v0 = acc[2 * o], v1 = acc[2 * o + 1];
-            if (a.flags & SC_OUT_RELU) {
-                v0 = fmaxf(v0, 0.f);
-                v1 = fmaxf(v1, 0.f);
+            for (int j = 0; j < 16; ++j) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wg + k * cout + 4 * j);
+                acc[4 * j] += v * w4.x; acc[4 * j + 1] += v * w4.y; acc[4 * j + 2] += v * w4.z; acc[4 * j + 3] += v * w4.w;
             }
-            hh[o] = __floats2half2_rn(v0, v1);
         }
-        *reinterpret_cast<uint4*>(a.y + p * a.ldy + cg * 8) = u;
+        __half* dst = a.y + p * a.ldy + cg * 64;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint4 u;
+            __half2* hh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                float v0 = acc[8 * j + 2 * o], v1 = acc[8 * j + 2 * o + 1];
+                if (a.flags & SC_OUT_RELU) {
+                    v0 = fmaxf(v0, 0.f);
+                    v1 = fmaxf(v1, 0.f);
+                }
+                hh[o] = __floats2half2_rn(v0, v1);
+            }
+            reinterpret_cast<uint4*>(dst)[j] = u;
+        }
     }
 }
 
 int smallconv_launch(const SmallConvArgs& a, cudaStream_t s) {
-    if ((a.cout & 7) || (a.ldy & 7) || (a.cin != 3 && a.cin != 4)) {
-        b2_set_error("smallconv: cin %d cout %d unsupported", a.cin, a.cout);
+    if ((a.cout & 63) || (a.ldy & 7) || (a.cin != 3 && a.cin != 4) || !a.wt) {
+        b2_set_error("smallconv: cin %d cout %d unsupported (cout must be a multiple of 64; prepared weights required)", a.cin, a.cout);
         return -1;
     }
     const size_t smem = ((size_t)a.cin * 9 * a.cout + a.cout) * sizeof(float);
-    const long total = (long)a.nb * a.h * a.w_ * (a.cout / 8);
-    long blocks = (total + 255) / 256;
+    const long total = (long)a.nb * a.h * a.w_ * (a.cout / 64);
+    long blocks = (total + 127) / 128;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    if (a.cin == 3) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(smallconv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        smallconv_kernel<3><<<(unsigned)blocks, 256, smem, s>>>(a);
-    } else {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(smallconv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        smallconv_kernel<4><<<(unsigned)blocks, 256, smem, s>>>(a);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(smallconv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(smallconv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        attr = true;
     }
+    if (a.cin == 3) smallconv_kernel<3><<<(unsigned)blocks, 128, smem, s>>>(a);
+    else smallconv_kernel<4><<<(unsigned)blocks, 128, smem, s>>>(a);
     B2_CHECK_LAUNCH("smallconv");
     return 0;
 }

@@ -17,10 +17,12 @@ struct GroupNormArgs {
     float eps;
     int silu;
     float* partial;   // workspace: groupnorm_partial_floats(nb, groups) floats (per-chunk group sums)
+    int* counters;    // 2*nb zero-initialised ints (grid barrier of the single-launch variant); null = two launches
 };
 // two launches: coalesced per-chunk statistics, then normalise (+SiLU); both fill the whole GPU
 int groupnorm_launch(const GroupNormArgs& a, cudaStream_t s);
 size_t groupnorm_partial_floats(int nb, int groups);
+int groupnorm_last_launch_count();  // 1 (cooperative single launch) or 2, for the most recent call on this thread
 
 // LayerNorm over the last dim of [rows][c] fp16 (eps 1e-5, affine), one warp per row.
 int layernorm_launch(const __half* x, int ldx, const float* gamma, const float* beta, __half* y, int ldy,
@@ -35,7 +37,7 @@ int upsample2x_launch(const __half* x, __half* y, int nb, int h, int w, int c, c
 enum : int { SC_IN_U8 = 1, SC_IN_TANH3 = 2, SC_OUT_RELU = 4, SC_IN_F32_NCHW = 8, SC_IN_F16_NCHW = 16 };
 struct SmallConvArgs {
     const void* x;       // fp16 NHWC [nb,h,w,cin] or u8 NHWC when SC_IN_U8
-    const __half* w;
+    const float* wt;     // fp32 [cin*9][cout], k = tap*cin + c (smallconv_prep_launch)
     const float* bias;
     __half* y; int ldy;  // NHWC [nb,h,w,cout]
     int nb, h, w_, cin, cout;
@@ -43,6 +45,8 @@ struct SmallConvArgs {
     int flags;
 };
 int smallconv_launch(const SmallConvArgs& a, cudaStream_t s);
+// OIHW fp16 -> fp32 [cin*9][cout] (once, at load time)
+int smallconv_prep_launch(const __half* w_oihw, float* wt, int cout, int cin, cudaStream_t s);
 
 // StreamDiffusion scheduler_step_batch + stream-batch buffer update (predict_x0_batch), fused.
 //   x0[i] = c_out[i] * (x[i] - beta[i]*eps[i]) / alpha[i] + c_skip[i] * x[i]

@@ -187,6 +187,19 @@ struct b2sd_engine {
         return d;
     }
 
+    // fp32 [cin*9][cout] weights of a tiny-Cin conv (cached)
+    const float* small_w(const std::string& key, cudaStream_t s) {
+        auto it = fvec.find("sw:" + key);
+        if (it != fvec.end()) return it->second;
+        const Raw* r = get(key);
+        if (!r) return nullptr;
+        const int cout = (int)r->shape[0], cin = (int)r->shape[1];
+        float* d = static_cast<float*>(weights.alloc((size_t)cin * 9 * cout * sizeof(float)));
+        if (!d || smallconv_prep_launch(r->p, d, cout, cin, s)) return nullptr;
+        fvec["sw:" + key] = d;
+        return d;
+    }
+
     struct ConvSeg { std::string key; int c0, cn, taps; };
     // packed [rows_pad][K] matrix, K = concat of segments each ordered [tap][c]
     __half* pack_conv(const std::string& name, const std::vector<ConvSeg>& segs, int rows, int* k_out,
@@ -307,7 +320,8 @@ struct b2sd_engine {
         a.y = y.p; a.ldy = y.ld;
         a.nb = xa.n; a.hw = xa.h * xa.w; a.groups = cfg.norm_groups; a.eps = eps; a.silu = silu;
         a.partial = gn_ws;
-        launches += 2;
+        a.counters = tile_counters;   // zero-initialised, self re-arming
+        launches += 1;
         prog_frame.push_back(Op([a](cudaStream_t s) { return groupnorm_launch(a, s); }, "groupnorm " + prefix));
         return 0;
     }
@@ -376,8 +390,13 @@ struct b2sd_engine {
     int build_program(cudaStream_t s);
     int run(std::vector<Op>& ops, cudaStream_t s) {
         static const bool dbg = getenv("B200SD_DEBUG_SYNC") != nullptr;
+        static const char* skip = getenv("B200SD_SKIP");  // debug: "groupnorm,attn" drops those launches (timing only)
         int idx = 0;
         for (auto& op : ops) {
+            if (skip) {
+                const std::string kind = op.name.substr(0, op.name.find(' '));
+                if (!kind.empty() && std::string(skip).find(kind) != std::string::npos) { ++idx; continue; }
+            }
             TRY(op(s));
             if (dbg) {
                 cudaError_t e = cudaStreamSynchronize(s);
@@ -639,10 +658,10 @@ int b2sd_engine::build_program(cudaStream_t s) {
     // ================= TAESD encoder (EncoderTiny) =================
     Act e = new_act(1, H, W, 64);
     {
-        const Raw* w0 = get("vae.encoder.layers.0.weight");
-        if (!w0) return -1;
         head = SmallConvArgs{};
-        head.w = w0->p; head.bias = vec({"vae.encoder.layers.0.bias"});
+        head.wt = small_w("vae.encoder.layers.0.weight", s);
+        if (!head.wt) return -1;
+        head.bias = vec({"vae.encoder.layers.0.bias"});
         head.y = e.p; head.ldy = e.ld; head.nb = 1; head.h = H; head.w_ = W; head.cin = 3; head.cout = 64;
         head.flags = SC_IN_U8;
         if (!head.bias) return -1;
@@ -679,10 +698,10 @@ int b2sd_engine::build_program(cudaStream_t s) {
     // ================= UNet2DConditionModel =================
     Act h = new_act(B, lh, lw, ch[0]);
     {
-        const Raw* w = get("conv_in.weight");
-        if (!w) return -1;
         SmallConvArgs a{};
-        a.x = x_in.p; a.w = w->p; a.bias = vec({"conv_in.bias"});
+        a.wt = small_w("conv_in.weight", s);
+        if (!a.wt) return -1;
+        a.x = x_in.p; a.bias = vec({"conv_in.bias"});
         a.y = h.p; a.ldy = h.ld; a.nb = B; a.h = lh; a.w_ = lw; a.cin = 4; a.cout = ch[0]; a.in_h = lh; a.in_w = lw;
         if (!a.bias) return -1;
         ++launches;
@@ -763,10 +782,10 @@ int b2sd_engine::build_program(cudaStream_t s) {
     // ================= TAESD decoder (DecoderTiny) =================
     Act dcur = new_act(1, lh, lw, 64);
     {
-        const Raw* w = get("vae.decoder.layers.0.weight");
-        if (!w) return -1;
         SmallConvArgs a{};
-        a.x = x0.p; a.w = w->p; a.bias = vec({"vae.decoder.layers.0.bias"});
+        a.wt = small_w("vae.decoder.layers.0.weight", s);
+        if (!a.wt) return -1;
+        a.x = x0.p; a.bias = vec({"vae.decoder.layers.0.bias"});
         a.y = dcur.p; a.ldy = dcur.ld; a.nb = 1; a.h = lh; a.w_ = lw; a.cin = 4; a.cout = 64; a.in_h = lh; a.in_w = lw;
         a.flags = SC_IN_TANH3 | SC_OUT_RELU;
         if (!a.bias) return -1;
