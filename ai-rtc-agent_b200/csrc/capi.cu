@@ -37,7 +37,8 @@ int b2sd_op_igemm(const b2sd_igemm_desc* d, void* stream) {
     g.Nb = d->nb; g.Ho = d->ho; g.Wo = d->wo;
     g.BN = d->bn;
     g.splits = d->splits;
-    g.partial = reinterpret_cast<float*>(d->partial);
+    g.partial = nullptr;
+    g.dbg_ts = reinterpret_cast<unsigned long long*>(d->partial);  // op-level entry: `partial` doubles as the debug timeline buffer
     g.epi.out = reinterpret_cast<__half*>(d->out);
     g.epi.ldc = d->ldc;
     g.epi.colbias = d->colbias;

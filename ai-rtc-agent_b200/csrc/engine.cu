@@ -302,9 +302,9 @@ struct b2sd_engine {
         }
         launches += 1;
         char label[256];
-        snprintf(label, sizeof(label), "igemm %s rows=%ld n=%d kb=%d bn=%d splits=%d grid=%u,%u,%u tile=%dx%dx%d", cur.c_str(),
+        snprintf(label, sizeof(label), "igemm %s rows=%ld n=%d kb=%d bn=%d splits=%d grid=%u,%u,%u %s", cur.c_str(),
                  plan.rows_total, d.epi.n_valid, plan.p.total_kb, plan.p.BN, plan.splits, plan.grid.x, plan.grid.y,
-                 plan.grid.z, plan.p.tn, plan.p.th, plan.p.tw);
+                 plan.grid.z, plan.mode == 1 ? (plan.c3.MT == 2 ? "halo16x16" : "halo16x8") : "taps");
         dst.push_back(Op([plan](cudaStream_t s) { return igemm_launch(plan, s); }, label,
                          2.0 * (double)plan.rows_total * n_gemm * plan.p.total_kb * IG_BK));
         return 0;

@@ -57,9 +57,38 @@ struct IgemmParams {
     uint32_t a_bytes;             // TMA box bytes of one A tile
     uint32_t b_bytes;
     uint32_t tmem_cols;
+    unsigned long long* dbg_ts;   // debug: 8 globaltimer stamps per CTA (null = off)
     float* partial;               // [splits][rows_total][n_pad] fp32 (split-K only)
     int* tile_counters;           // one int per (m tile, n tile), zero between launches (split-K only)
     int n_pad;
+    IgEpilogue epi;
+};
+
+// ---- halo-reuse 3x3 convolution (stride 1): one TMA load of a (16+2) x (TW+2) pixel halo tile per 64-channel
+// block feeds all nine filter taps (shifted UMMA descriptors), and MT = 1 or 2 M-tiles of 128 pixels share every
+// weight tile.  Cuts L2->SM operand traffic ~4x versus nine independent tap loads per M-tile.
+constexpr int C3_THREADS = 224;   // warp0: B (weights) TMA, warp1: MMA, warps 2-5: epilogue, warp6: A (halo) TMA
+constexpr int C3_TH = 16;         // output rows per tile; tile width = 8 * MT
+constexpr int C3_MAX_BSTAGES = 8;
+struct Conv3Params {
+    CUtensorMap tmA[IG_MAX_SRC];
+    CUtensorMap tmB;
+    int seg_ntap[IG_MAX_SRC];
+    int seg_cblocks[IG_MAX_SRC];
+    int seg_koff[IG_MAX_SRC];     // K offset (elements) of the segment inside a packed weight row
+    int seg_c[IG_MAX_SRC];        // channels of the segment
+    uint32_t seg_abytes[IG_MAX_SRC];
+    int nseg;
+    int units_total;              // sum of cblocks: one unit = one halo tile + its taps
+    int units_per_split;
+    int MT, BN;
+    int tiles_w, tiles_h;
+    int Wo, Ho, Nb;
+    int num_bstages;
+    uint32_t abuf_bytes;          // one A buffer (1024-aligned)
+    uint32_t b_bytes;
+    uint32_t tmem_cols;
+    unsigned long long* dbg_ts;
     IgEpilogue epi;
 };
 
@@ -80,12 +109,15 @@ struct IgemmDesc {
     int Nb, Ho, Wo;
     int BN;           // 0 = auto
     int splits;       // 0/1 = none
+    unsigned long long* dbg_ts;  // optional per-CTA timeline (8 stamps per CTA)
     float* partial;   // workspace for split-K (size splits*rows*n_pad floats)
     int* tile_counters;  // >= m_tiles*n_tiles zero-initialised ints (self re-arming)
     IgEpilogue epi;
 };
 
 struct IgemmPlan {
+    int mode;       // 0: igemm_kernel (tap-by-tap loads), 1: conv3_kernel (halo reuse)
+    Conv3Params c3;
     IgemmParams p;
     dim3 grid;
     size_t smem;

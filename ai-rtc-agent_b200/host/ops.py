@@ -31,7 +31,7 @@ def _view(t: torch.Tensor) -> capi.ActView:
 def igemm(srcs: Sequence[Tuple[torch.Tensor, int]], w: torch.Tensor, out: torch.Tensor, *,
           stride: int = 1, colbias: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
           acc_scale: float = 1.0, res_scale: float = 1.0, relu: bool = False, geglu: bool = False,
-          bn: int = 0, splits: int = 1, n_valid: Optional[int] = None) -> torch.Tensor:
+          bn: int = 0, splits: int = 1, n_valid: Optional[int] = None, timeline: Optional[torch.Tensor] = None) -> torch.Tensor:
     """srcs: [(NHWC fp16 tensor, ntap)], w: packed fp16 [rows, K]; out: NHWC fp16 [nb,ho,wo,ldc>=n]."""
     d = capi.IgemmDesc()
     d.nseg = len(srcs)
@@ -47,12 +47,8 @@ def igemm(srcs: Sequence[Tuple[torch.Tensor, int]], w: torch.Tensor, out: torch.
     d.out, d.ldc = out.data_ptr(), out.stride(2)
     nv = n_valid if n_valid is not None else out.shape[3]
     d.n_valid = nv
-    if splits > 1:
-        nfl = capi.lib().b2sd_igemm_partial_floats(splits, nb * ho * wo, nv)
-        part = _SCRATCH.get((nfl, out.device))
-        if part is None:
-            part = _SCRATCH[(nfl, out.device)] = torch.empty(nfl, dtype=torch.float32, device=out.device)
-        d.partial = part.data_ptr()
+    if timeline is not None:
+        d.partial = timeline.data_ptr()   # debug: int64 tensor [ctas, 8] receiving globaltimer stamps (tap kernel only)
     if colbias is not None:
         assert colbias.dtype == torch.float32 and colbias.is_contiguous()
         d.colbias = colbias.data_ptr()

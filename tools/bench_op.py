@@ -22,6 +22,14 @@ def conv_case(nb, h, w, cin, cout, bn, splits, res=False, relu=False):
     us = timeit(lambda: ops.igemm([(x, 9)], wt, y, colbias=b, bn=bn, splits=splits, res=x if res else None, relu=relu))
     fl = 2.0 * nb * h * w * cout * cin * 9
     print(f"conv {nb}x{h}x{w} {cin}->{cout} bn={bn} splits={splits}: {us:8.1f} us  {fl/us/1e6:7.1f} TF/s")
+import itertools
+if "sweep" in sys.argv:
+    for (h, c) in [(64, 320), (32, 640), (16, 1280), (8, 1280)]:
+        for bn, sp in itertools.product([64, 128, 160, 256], [1, 2, 4, 8]):
+            if c % bn: continue
+            try: conv_case(1, h, h, c, c, bn, sp)
+            except Exception as e: print("fail", h, c, bn, sp, str(e)[:80])
+    sys.exit(0)
 for args in [(1,512,512,64,64,64,1,True,True), (1,256,256,64,64,64,1,True,True), (1,64,64,320,320,64,1), (1,64,64,320,320,160,1),
              (1,32,32,640,640,64,1), (1,32,32,640,640,64,2), (1,32,32,640,640,128,2), (1,16,16,1280,1280,64,1), (1,16,16,1280,1280,64,4),
              (1,16,16,1280,1280,128,8), (1,16,16,1280,1280,256,8), (1,8,8,1280,1280,64,8), (1,8,8,1280,1280,64,16), (1,16,16,2560,1280,64,4)]:
