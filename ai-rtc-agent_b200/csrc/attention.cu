@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include "igemm.cuh"  // b2_set_error
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace b2 {
@@ -88,6 +89,8 @@ __global__ void __launch_bounds__(AT_THREADS) attn_kernel(const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();   // the next kernel may start its own prologue now
+    pdl_wait();                // ... and everything below reads the previous kernel's output
 
     if (warp == 0) {
         if (lane == 0) {
@@ -355,10 +358,10 @@ int attn_launch(const AttnPlan& plan, cudaStream_t s) {
     p.sq = d.sq; p.skv = d.skv; p.heads = d.heads; p.d_real = d.d_real;
     p.k_bstride = d.k_bstride; p.vt_bstride = d.vt_bstride;
     p.scale_log2 = (float)(1.4426950408889634 / sqrt((double)d.d_real));
-    if (d.dp == 64) attn_kernel<1, 128><<<plan.grid, AT_THREADS, plan.smem, s>>>(p);
-    else if (d.dp == 128) attn_kernel<2, 128><<<plan.grid, AT_THREADS, plan.smem, s>>>(p);
-    else attn_kernel<3, 64><<<plan.grid, AT_THREADS, plan.smem, s>>>(p);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e;
+    if (d.dp == 64) e = launch_k(attn_kernel<1, 128>, plan.grid, dim3(AT_THREADS), plan.smem, s, 1, p);
+    else if (d.dp == 128) e = launch_k(attn_kernel<2, 128>, plan.grid, dim3(AT_THREADS), plan.smem, s, 1, p);
+    else e = launch_k(attn_kernel<3, 64>, plan.grid, dim3(AT_THREADS), plan.smem, s, 1, p);
     if (e != cudaSuccess) {
         b2_set_error("attn launch: %s", cudaGetErrorString(e));
         return -1;

@@ -4,8 +4,24 @@
 #include <stdio.h>
 
 #include "igemm.cuh"  // b2_set_error
+#include "launch.cuh"
 
 namespace b2 {
+
+#define B2_PDL_ENTRY()            \
+    do {                          \
+        pdl_launch_dependents();  \
+        pdl_wait();               \
+    } while (0)
+
+#define B2_LAUNCHED(name, expr)                                            \
+    do {                                                                   \
+        cudaError_t e__ = (expr);                                          \
+        if (e__ != cudaSuccess) {                                          \
+            b2_set_error("%s launch: %s", name, cudaGetErrorString(e__));  \
+            return -1;                                                     \
+        }                                                                  \
+    } while (0)
 
 #define B2_CHECK_LAUNCH(name)                                              \
     do {                                                                   \
@@ -50,6 +66,7 @@ __device__ __forceinline__ T block_reduce_sum(T v, T* scratch) {
 constexpr int GN_MAX_CHUNKS = 128;
 
 __global__ void __launch_bounds__(512) gn_stats_kernel(GroupNormArgs a, int ppc, int vc, int rpi) {
+    B2_PDL_ENTRY();
     extern __shared__ float sm[];  // [rpi][C][2] then reused as [C][2]
     const int C = a.ca + a.cb;
     const int chunk = blockIdx.x, b = blockIdx.y;
@@ -132,6 +149,7 @@ __device__ __forceinline__ void gn_finalize_stats(const GroupNormArgs& a, int b,
 }
 
 __global__ void __launch_bounds__(256) gn_apply_kernel(GroupNormArgs a, int nchunks, long vec_per_batch) {
+    B2_PDL_ENTRY();
     __shared__ float s_mean[64], s_rstd[64];
     __shared__ float s_scratch[16 * 64 * 2];
     const int C = a.ca + a.cb;
@@ -183,6 +201,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GroupNormArgs a, int nchu
 // between launches (the last CTA to leave re-arms them).
 constexpr int GN_CACHE = 12;
 __global__ void __launch_bounds__(512) gn_fused_kernel(GroupNormArgs a, int ppc, int vc, int rpi, int* counters) {
+    B2_PDL_ENTRY();
     extern __shared__ float sm[];
     __shared__ float s_mean[64], s_rstd[64];
     const int C = a.ca + a.cb;
@@ -353,14 +372,12 @@ int groupnorm_launch(const GroupNormArgs& a, cudaStream_t s) {
         g_gn_last_launches = 1;
         return 0;
     }
-    gn_stats_kernel<<<dim3(nchunks, a.nb), threads, smem, s>>>(a, ppc, vc, rpi);
-    B2_CHECK_LAUNCH("gn_stats");
+    B2_LAUNCHED("gn_stats", launch_k(gn_stats_kernel, dim3(nchunks, a.nb), dim3(threads), smem, s, 1, a, ppc, vc, rpi));
     const long vec_per_batch = (long)a.hw * vc;
     long blocks = (vec_per_batch + 255) / 256;
     const long cap = (148 * 4 + a.nb - 1) / a.nb;
     if (blocks > cap) blocks = cap;
-    gn_apply_kernel<<<dim3((unsigned)blocks, a.nb), 256, 0, s>>>(a, nchunks, vec_per_batch);
-    B2_CHECK_LAUNCH("gn_apply");
+    B2_LAUNCHED("gn_apply", launch_k(gn_apply_kernel, dim3((unsigned)blocks, a.nb), dim3(256), 0, s, 1, a, nchunks, vec_per_batch));
     g_gn_last_launches = 2;
     return 0;
 }
@@ -369,6 +386,7 @@ int groupnorm_launch(const GroupNormArgs& a, cudaStream_t s) {
 __global__ void layernorm_kernel(const __half* __restrict__ x, int ldx, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, __half* __restrict__ y, int ldy, long rows,
                                  int c, float eps) {
+    B2_PDL_ENTRY();
     const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -416,13 +434,14 @@ int layernorm_launch(const __half* x, int ldx, const float* gamma, const float* 
         return -1;
     }
     const int wpb = 8;
-    layernorm_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, s>>>(x, ldx, gamma, beta, y, ldy, rows, c, eps);
-    B2_CHECK_LAUNCH("layernorm");
+    B2_LAUNCHED("layernorm", launch_k(layernorm_kernel, dim3((unsigned)((rows + wpb - 1) / wpb)), dim3(wpb * 32), 0, s, 1, x, ldx, gamma,
+                                      beta, y, ldy, rows, c, eps));
     return 0;
 }
 
 // ------------------------------------------------------------------------------------------ upsample
 __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int nb, int h, int w, int c8) {
+    B2_PDL_ENTRY();
     const long total = (long)nb * (2 * h) * (2 * w) * c8;
     for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
         const int cc = (int)(e % c8);
@@ -444,9 +463,8 @@ int upsample2x_launch(const __half* x, __half* y, int nb, int h, int w, int c, c
     const int threads = 256;
     long blocks = (total + threads - 1) / threads;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    upsample2x_kernel<<<(unsigned)blocks, threads, 0, s>>>(reinterpret_cast<const uint4*>(x),
-                                                           reinterpret_cast<uint4*>(y), nb, h, w, c / 8);
-    B2_CHECK_LAUNCH("upsample2x");
+    B2_LAUNCHED("upsample2x", launch_k(upsample2x_kernel, dim3((unsigned)blocks), dim3(threads), 0, s, 1,
+                                       reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), nb, h, w, c / 8));
     return 0;
 }
 
@@ -469,6 +487,7 @@ int smallconv_prep_launch(const __half* w_oihw, float* wt, int cout, int cin, cu
 
 template <int CIN>
 __global__ void __launch_bounds__(128) smallconv_kernel(SmallConvArgs a) {
+    B2_PDL_ENTRY();
     extern __shared__ float ws[];  // [CIN*9][cout] then bias[cout]
     constexpr int K = CIN * 9;
     const int cout = a.cout;
@@ -569,9 +588,8 @@ int smallconv_launch(const SmallConvArgs& a, cudaStream_t s) {
         cudaFuncSetAttribute(smallconv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         attr = true;
     }
-    if (a.cin == 3) smallconv_kernel<3><<<(unsigned)blocks, 128, smem, s>>>(a);
-    else smallconv_kernel<4><<<(unsigned)blocks, 128, smem, s>>>(a);
-    B2_CHECK_LAUNCH("smallconv");
+    if (a.cin == 3) B2_LAUNCHED("smallconv", launch_k(smallconv_kernel<3>, dim3((unsigned)blocks), dim3(128), smem, s, 1, a));
+    else B2_LAUNCHED("smallconv", launch_k(smallconv_kernel<4>, dim3((unsigned)blocks), dim3(128), smem, s, 1, a));
     return 0;
 }
 
@@ -579,6 +597,7 @@ int smallconv_launch(const SmallConvArgs& a, cudaStream_t s) {
 __global__ void lcm_step_kernel(__half* __restrict__ x, const __half* __restrict__ eps,
                                 const __half* __restrict__ noise, const float* __restrict__ coef,
                                 __half* __restrict__ out_latent, int T, int hw, int do_add_noise) {
+    B2_PDL_ENTRY();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= hw) return;
     const float* alpha = coef;
@@ -629,13 +648,14 @@ __global__ void lcm_step_kernel(__half* __restrict__ x, const __half* __restrict
 
 int lcm_step_launch(__half* x, const __half* eps, const __half* noise, const float* coef, __half* out_latent,
                     int T, int hw, int do_add_noise, cudaStream_t s) {
-    lcm_step_kernel<<<(hw + 127) / 128, 128, 0, s>>>(x, eps, noise, coef, out_latent, T, hw, do_add_noise);
-    B2_CHECK_LAUNCH("lcm_step");
+    B2_LAUNCHED("lcm_step", launch_k(lcm_step_kernel, dim3((hw + 127) / 128), dim3(128), 0, s, 1, x, eps, noise, coef, out_latent, T, hw,
+                                     do_add_noise));
     return 0;
 }
 
 // ------------------------------------------------------------------------------------------ post
 __global__ void post_u8_kernel(const __half* __restrict__ y, int ldy, uint8_t* __restrict__ out, int nb, int h, int w) {
+    B2_PDL_ENTRY();
     const long hw = (long)h * w;
     const long total = (long)nb * hw;
     const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -657,6 +677,7 @@ __global__ void post_u8_kernel(const __half* __restrict__ y, int ldy, uint8_t* _
 }
 
 __global__ void post_f16_kernel(const __half* __restrict__ y, int ldy, __half* __restrict__ out, int nb, int h, int w) {
+    B2_PDL_ENTRY();
     const long hw = (long)h * w;
     const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= (long)nb * hw) return;
@@ -669,15 +690,13 @@ __global__ void post_f16_kernel(const __half* __restrict__ y, int ldy, __half* _
 
 int post_f16_launch(const __half* y_nhwc, int ldy, __half* out_nchw, int nb, int h, int w, cudaStream_t s) {
     const long total = (long)nb * h * w;
-    post_f16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(y_nhwc, ldy, out_nchw, nb, h, w);
-    B2_CHECK_LAUNCH("post_f16");
+    B2_LAUNCHED("post_f16", launch_k(post_f16_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, 1, y_nhwc, ldy, out_nchw, nb, h, w));
     return 0;
 }
 
 int post_u8_launch(const __half* y_nhwc, int ldy, uint8_t* out_nchw, int nb, int h, int w, cudaStream_t s) {
     const long total = (long)nb * h * w;
-    post_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(y_nhwc, ldy, out_nchw, nb, h, w);
-    B2_CHECK_LAUNCH("post_u8");
+    B2_LAUNCHED("post_u8", launch_k(post_u8_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, 1, y_nhwc, ldy, out_nchw, nb, h, w));
     return 0;
 }
 

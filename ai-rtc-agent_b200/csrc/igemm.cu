@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace b2 {
@@ -251,6 +252,8 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();   // the next kernel may start its own prologue now
+    pdl_wait();                // ... and everything below reads the previous kernel's output
     if (ts && threadIdx.x == 0) ts[1] = globaltimer_ns();
 
     if (warp == 0) {
@@ -484,6 +487,8 @@ __global__ void __launch_bounds__(C3_THREADS) conv3_kernel(const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();   // the next kernel may start its own prologue now
+    pdl_wait();                // ... and everything below reads the previous kernel's output
     if (ts && threadIdx.x == 0) ts[1] = globaltimer_ns();
 
     // unit -> (segment, channel block)
@@ -998,23 +1003,9 @@ int igemm_init() {
 
 int igemm_launch(const IgemmPlan& plan, cudaStream_t stream) {
     if (igemm_init()) return -1;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = plan.grid;
-    cfg.blockDim = dim3(plan.mode == 1 ? C3_THREADS : IG_THREADS);
-    cfg.dynamicSmemBytes = plan.smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    if (plan.splits > 1) {
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 1;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = (unsigned)plan.splits;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-    }
-    cudaError_t e = plan.mode == 1 ? cudaLaunchKernelEx(&cfg, conv3_kernel, plan.c3)
-                                   : cudaLaunchKernelEx(&cfg, igemm_kernel, plan.p);
-    if (e == cudaSuccess) e = cudaGetLastError();
+    const int cz = plan.splits > 1 ? plan.splits : 1;
+    cudaError_t e = plan.mode == 1 ? launch_k(conv3_kernel, plan.grid, dim3(C3_THREADS), plan.smem, stream, cz, plan.c3)
+                                   : launch_k(igemm_kernel, plan.grid, dim3(IG_THREADS), plan.smem, stream, cz, plan.p);
     if (e != cudaSuccess) {
         b2_set_error("igemm launch: %s", cudaGetErrorString(e));
         return -1;

@@ -97,8 +97,7 @@ def run_oracle(steps: int, warmup: int, budget_s: float):
     from oracle import stream as ostream
     from oracle import unet as ounet
     from oracle import weights as ow
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
+    threads = torch.get_num_threads()   # torch's default = physical cores; oversubscribing the SMT siblings is slower
     cfg = ounet.SD_TURBO
     usd = ow.to_float(ow.make_unet_weights(cfg))
     vsd = ow.to_float(ow.make_taesd_weights())
@@ -228,11 +227,18 @@ def main_gpu(args):
     ig_tflops = ig["flops"] / (ig["ms"] * 1e-3) / 1e12
     eager_ms = sum(op["ms"] for op in prof)
     step_tflops = GFLOP_PER_FRAME * (value / world) / 1e3
+    traffic, traffic_note = None, "no ncu capture found under profiles/"
+    tpath = os.path.join(ROOT, "profiles", "igemm_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic, traffic_note = tj.get("dram_bytes_per_launch"), tj.get("note", "")
     roofline = {
         "bound": "tensor", "kernel": "igemm_kernel (tcgen05 implicit-GEMM conv/linear)",
         "achieved": ig_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-        "frac": ig_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
+        "frac": ig_tflops / peaks["bf16_tflops_sustained"], "traffic": traffic,
         "peak_source": peak_src + ", sustained figure (kernel timed inside a long step)",
+        "traffic_note": traffic_note,
         "kernel_share_of_step": ig["ms"] / eager_ms, "kernel_launches_per_step": ig["launches"],
         "kernel_algorithmic_gflop_per_step": ig["flops"] / 1e9,
         "step_achieved": step_tflops, "step_frac": step_tflops / peaks["bf16_tflops_sustained"],
