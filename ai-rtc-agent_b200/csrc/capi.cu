@@ -36,6 +36,7 @@ int b2sd_op_igemm(const b2sd_igemm_desc* d, void* stream) {
     g.stride = d->stride;
     g.Nb = d->nb; g.Ho = d->ho; g.Wo = d->wo;
     g.BN = d->bn;
+    g.swap = d->swap;
     g.splits = d->splits;
     g.partial = nullptr;
     g.dbg_ts = reinterpret_cast<unsigned long long*>(d->partial);  // op-level entry: `partial` doubles as the debug timeline buffer

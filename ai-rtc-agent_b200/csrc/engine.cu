@@ -140,6 +140,7 @@ struct b2sd_engine {
     bool built = false;
     int launches = 0;
     std::string cur;   // name prefix of the layer being built (debug / profiling labels)
+    bool allow_swap = false;  // builders enable the swapped GEMM orientation for UNet contractions (never TAESD / V^T / GEGLU)
     cudaGraphExec_t graph_exec = nullptr;
     cudaGraph_t graph = nullptr;
 
@@ -264,6 +265,34 @@ struct b2sd_engine {
     int add_igemm(std::vector<Op>& dst, IgemmDesc d) {
         const bool geglu = (d.epi.flags & IG_GEGLU) != 0;
         const int n_gemm = geglu ? 2 * d.epi.n_valid : d.epi.n_valid;
+        static const bool swap_on = getenv("B2_SWAP") != nullptr;
+        if (swap_on && allow_swap && !geglu && d.epi.n_valid >= 128) {
+            // Swapped orientation (weights on the M side): at batch 1 the UNet has few pixels but many channels, so this is
+            // the way to issue wide (N = 256 pixel) MMAs, read every weight exactly once and still fill the machine.
+            IgemmPlan plan;
+            const long rows = (long)d.Nb * d.Ho * d.Wo;
+            d.swap = 1;
+            d.BN = rows >= 256 ? 256 : (rows >= 128 ? 128 : 64);
+            d.splits = 1; d.partial = nullptr;
+            TRY(igemm_plan(d, &plan));
+            const long ctas = (long)plan.grid.x * plan.grid.y;
+            int max_by_k = plan.p.total_kb / 4;
+            if (max_by_k < 1) max_by_k = 1;
+            if (max_by_k > 8) max_by_k = 8;
+            int splits = 1;
+            while (splits * 2 <= max_by_k && ctas * splits * 2 <= 192) splits *= 2;
+            if (splits > 1) {
+                d.splits = splits;
+                TRY(igemm_plan(d, &plan));
+            }
+            launches += 1;
+            char label[256];
+            snprintf(label, sizeof(label), "igemm %s rows=%ld n=%d kb=%d bn=%d splits=%d grid=%u,%u,%u swapped", cur.c_str(),
+                     plan.rows_total, d.epi.n_valid, plan.p.total_kb, plan.p.BN, plan.splits, plan.grid.x, plan.grid.y, plan.grid.z);
+            dst.push_back(Op([plan](cudaStream_t s) { return igemm_launch(plan, s); }, label,
+                             2.0 * (double)plan.rows_total * n_gemm * plan.p.total_kb * IG_BK));
+            return 0;
+        }
         static const int cands[] = {256, 160, 128, 64, 32, 16};
         int best_bn = 0;
         IgemmPlan plan;
@@ -416,6 +445,7 @@ struct b2sd_engine {
 // ResnetBlock2D (diffusers resnet.py): GN+SiLU -> conv1 (+temb) -> GN+SiLU -> conv2, + shortcut(x)
 int b2sd_engine::build_resnet(const std::string& p, const Act& xa, const Act* xb, int cout, Act* out, cudaStream_t s) {
     cur = p;
+    allow_swap = true;
     const int cin = xa.c + (xb ? xb->c : 0);
     const int B = xa.n;
     Act n1 = new_act(B, xa.h, xa.w, cin);
@@ -483,6 +513,7 @@ int b2sd_engine::build_resnet(const std::string& p, const Act& xa, const Act* xb
 // Transformer2DModel + BasicTransformerBlock (diffusers transformer_2d.py / attention.py)
 int b2sd_engine::build_transformer(const std::string& p, const Act& x, int heads, Act* out, cudaStream_t s) {
     cur = p;
+    allow_swap = true;
     const int B = x.n, C = x.c, HW = x.h * x.w;
     const long M = (long)B * HW;
     const int d_real = C / heads;
@@ -520,6 +551,7 @@ int b2sd_engine::build_transformer(const std::string& p, const Act& x, int heads
     __half* vt = static_cast<__half*>(prog.alloc((size_t)Cp * vt_ld * 2));
     if (!vt) return -1;
     cudaMemsetAsync(vt, 0, (size_t)Cp * vt_ld * 2, s);  // pad columns must stay finite (0 * NaN = NaN in P.V)
+    allow_swap = false;  // V^T already has the weights on the M side
     for (int bi = 0; bi < (one_gemm ? 1 : B); ++bi) {
         ActView wv_view{wv, 1, 1, Cp, C, C};
         IgemmDesc d{};
@@ -532,6 +564,7 @@ int b2sd_engine::build_transformer(const std::string& p, const Act& x, int heads
         d.epi.n_valid = one_gemm ? (int)M : HW;
         TRY(add_igemm(prog_frame, d));
     }
+    allow_swap = true;
     Act ao = new_act(B, x.h, x.w, C);
     {
         AttnDesc a{};
@@ -561,6 +594,7 @@ int b2sd_engine::build_transformer(const std::string& p, const Act& x, int heads
     const int Lpad = 128 * ((L + 127) / 128);
     __half* vct = static_cast<__half*>(prog.alloc((size_t)Cp * Lpad * 2));
     {
+        allow_swap = false;
         ActView ctxv{ctx, 1, 1, L, D, D};
         TRY(add_linear(prog_prompt, ctxv, wk2, Cp, D, nullptr, kc, Cp, nullptr, 0));
         ActView wvv{wv2, 1, 1, Cp, D, D};
@@ -570,6 +604,7 @@ int b2sd_engine::build_transformer(const std::string& p, const Act& x, int heads
         d.Nb = 1; d.Ho = 1; d.Wo = Cp;
         d.epi.out = vct; d.epi.ldc = Lpad; d.epi.acc_scale = 1.f; d.epi.res_scale = 1.f; d.epi.n_valid = L;
         TRY(add_igemm(prog_prompt, d));
+        allow_swap = true;
     }
     Act q2 = new_act(1, 1, (int)M, Cp);
     TRY(add_linear(prog_frame, tokens(ln2), wq2, Cp, C, nullptr, q2.p, Cp, nullptr, 0));
@@ -637,6 +672,7 @@ int b2sd_engine::build_transformer(const std::string& p, const Act& x, int heads
 // AutoencoderTinyBlock: relu(conv(relu(conv(relu(conv(x))))) + x)
 int b2sd_engine::build_taesd_block(const std::string& p, const Act& x, Act* out, cudaStream_t s) {
     cur = p;
+    allow_swap = false;
     Act a = new_act(x.n, x.h, x.w, x.c), b = new_act(x.n, x.h, x.w, x.c);
     *out = new_act(x.n, x.h, x.w, x.c);
     TRY(add_conv(prog_frame, x, p + ".conv.0.weight", p + ".conv.0.bias", 9, 1, a, IG_RELU, nullptr, s));
@@ -655,6 +691,7 @@ int b2sd_engine::build_program(cudaStream_t s) {
     const int* ch = cfg.block_out_channels;
     const int nlev = 4;
 
+    allow_swap = false;
     // ================= TAESD encoder (EncoderTiny) =================
     Act e = new_act(1, H, W, 64);
     {
@@ -695,6 +732,7 @@ int b2sd_engine::build_program(cudaStream_t s) {
     }
     taps["unet_in"] = x_in;
 
+    allow_swap = true;
     // ================= UNet2DConditionModel =================
     Act h = new_act(B, lh, lw, ch[0]);
     {
@@ -779,6 +817,7 @@ int b2sd_engine::build_program(cudaStream_t s) {
         prog_frame.push_back(Op([=](cudaStream_t st) { return lcm_step_launch(xp, ep, np_, cf, op, T, hw, dan, st); }, "lcm_step"));
     }
     taps["x0"] = x0;
+    allow_swap = false;
     // ================= TAESD decoder (DecoderTiny) =================
     Act dcur = new_act(1, lh, lw, 64);
     {

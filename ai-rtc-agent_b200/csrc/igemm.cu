@@ -207,6 +207,32 @@ __device__ __forceinline__ bool epi_fast_ok(const IgEpilogue& e) {
            (e.colbias_bstride & 3) == 0;
 }
 
+// Swapped orientation: the accumulator row is an output CHANNEL, its columns are the pixels of the tile.  16
+// consecutive pixel columns [j0, j0+16) of channel `cout`; consecutive lanes hold consecutive channels, so a warp's
+// 2-byte stores cover 64 contiguous bytes of one pixel row.
+__device__ __forceinline__ void epi_swap16(const IgemmParams& p, const float (&acc)[16], int cout, bool cout_ok, int j0,
+                                           int n0, int h0, int w0) {
+    const IgEpilogue& e = p.epi;
+    const int tw = 1 << p.tw_log2, th = 1 << p.th_log2;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int j = j0 + i;
+        const int wi = j & (tw - 1);
+        const int hi = (j >> p.tw_log2) & (th - 1);
+        const int ni = j >> (p.tw_log2 + p.th_log2);
+        const int n = n0 + ni, h = h0 + hi, w = w0 + wi;
+        if (cout_ok && ni < p.tn && n < p.Nb && h < p.Ho && w < p.Wo) {
+            const long orow = ((long)n * p.Ho + h) * p.Wo + w;
+            float v = acc[i];
+            if (e.colbias) v += e.colbias[(long)n * e.colbias_bstride + cout];
+            v *= e.acc_scale;
+            if (e.res) v += e.res_scale * __half2float(e.res[orow * e.ldr + cout]);
+            if (e.flags & IG_RELU) v = fmaxf(v, 0.f);
+            e.out[orow * e.ldc + cout] = __float2half_rn(v);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant__ IgemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -278,9 +304,10 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                     dy = tap / 3 - 1;
                     dx = tap % 3 - 1;
                 }
-                tma_load_4d(sa, &p.tmA[seg], &full_bar[stage], p.seg_c0[seg] + cb * IG_BK,
+                // normal: pixels -> A (M side), weights -> B.  swapped: weights (128 output channels) -> A, pixels -> B
+                tma_load_4d(p.swap ? sb : sa, &p.tmA[seg], &full_bar[stage], p.seg_c0[seg] + cb * IG_BK,
                             w0 * p.stride + dx, h0 * p.stride + dy, n0);
-                tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * IG_BK, ntile * p.BN);
+                tma_load_2d(p.swap ? sa : sb, &p.tmB, &full_bar[stage], kb * IG_BK, ntile * (p.swap ? IG_BM : p.BN));
                 if (ts && kb == kb_begin) ts[2] = globaltimer_ns();
                 if (++cb == p.seg_cblocks[seg]) {
                     cb = 0;
@@ -341,7 +368,35 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
         const long orow = ((long)n * p.Ho + h) * p.Wo + w;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
         const IgEpilogue& e = p.epi;
-        if (epi_fast_ok(e)) {
+        if (p.swap) {
+            const int cout = ntile * IG_BM + r;
+            const bool cout_ok = cout < e.n_valid;
+            mbar_wait(tmem_full_bar, 0);
+            tc_fence_after();
+            if (e.flags & IG_SPLITK) {
+                float4* stg = reinterpret_cast<float4*>(smem);
+                for (int c = 0; c < p.BN; c += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + c, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        stg[((c >> 2) + i) * IG_BM + r] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                                      __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                }
+            } else {
+                for (int c = 0; c < p.BN; c += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + c, v);
+                    tmem_ld_wait();
+                    float acc[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(v[i]);
+                    epi_swap16(p, acc, cout, cout_ok, c, n0, h0, w0);
+                }
+            }
+            if (ts && threadIdx.x == 64) ts[5] = globaltimer_ns();
+        } else if (epi_fast_ok(e)) {
             int ncols = e.n_valid - ntile * p.BN;
             if (ncols > p.BN) ncols = p.BN;
             epi_row_fast(e, taddr, ncols, ntile * p.BN, n, orow, row_ok && ncols > 0, tmem_full_bar);
@@ -425,7 +480,8 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                         acc[4 * i] += v.x; acc[4 * i + 1] += v.y; acc[4 * i + 2] += v.z; acc[4 * i + 3] += v.w;
                     }
                 }
-                if (ok) epi_store16<0>(p.epi, acc, n, ((long)n * p.Ho + h) * p.Wo + w, ntile * p.BN + cc * 16);
+                if (p.swap) epi_swap16(p, acc, ntile * IG_BM + r, ntile * IG_BM + r < p.epi.n_valid, cc * 16, n0, h0, w0);
+                else if (ok) epi_store16<0>(p.epi, acc, n, ((long)n * p.Ho + h) * p.Wo + w, ntile * p.BN + cc * 16);
             }
         }
         cluster_sync_all();  // nobody may exit while a peer still reads its shared memory
@@ -836,8 +892,101 @@ static int plan_halo(const IgemmDesc& d, int BN, int n_tiles, int splits_req, Ig
     return 0;
 }
 
+// Swapped orientation plan: output channels on the M side (128 per CTA), a tile of BN pixels on the N side.
+static int plan_swap(const IgemmDesc& d, IgemmPlan* plan) {
+    IgemmParams& p = plan->p;
+    if ((d.epi.flags & IG_GEGLU) || d.nseg < 1 || d.nseg > IG_MAX_SRC) {
+        b2_set_error("igemm(swap): unsupported (GEGLU / nseg %d)", d.nseg);
+        return -1;
+    }
+    int BN = d.BN;
+    const long rows_total = (long)d.Nb * d.Ho * d.Wo;
+    if (BN <= 0) BN = rows_total >= 256 ? 256 : (rows_total >= 128 ? 128 : 64);
+    if (BN != 64 && BN != 128 && BN != 256) {
+        b2_set_error("igemm(swap): BN %d must be 64, 128 or 256", BN);
+        return -1;
+    }
+    p.swap = 1;
+    p.BN = BN;
+    auto lg = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
+    int tw, th, tn;
+    if (d.Ho == 1 && d.Nb == 1) { tw = BN; th = 1; tn = 1; }
+    else if (d.Wo >= 16) { tw = 16; th = BN / 16; tn = 1; }
+    else { tw = 8; th = 8; tn = BN / 64; }
+    p.tw = tw; p.th = th; p.tn = tn;
+    p.tw_log2 = lg(tw); p.th_log2 = lg(th);
+    p.tiles_w = (d.Wo + tw - 1) / tw;
+    p.tiles_h = (d.Ho + th - 1) / th;
+    p.tiles_n = (d.Nb + tn - 1) / tn;
+    p.Wo = d.Wo; p.Ho = d.Ho; p.Nb = d.Nb;
+    p.stride = d.stride < 1 ? 1 : d.stride;
+    p.nseg = d.nseg;
+    int total_kb = 0;
+    for (int s = 0; s < d.nseg; ++s) {
+        const ActView& a = d.src[s];
+        if (a.C % IG_BK != 0 || (a.ld % 8) != 0 || (reinterpret_cast<uintptr_t>(a.ptr) & 15) || (d.ntap[s] != 1 && d.ntap[s] != 9)) {
+            b2_set_error("igemm(swap): bad source %d", s);
+            return -1;
+        }
+        p.seg_ntap[s] = d.ntap[s];
+        p.seg_cblocks[s] = a.C / IG_BK;
+        p.seg_c0[s] = 0;
+        total_kb += d.ntap[s] * p.seg_cblocks[s];
+        if (encode_act_map(&p.tmA[s], a, IG_BK, tw * p.stride, th * p.stride, tn, p.stride)) return -1;
+    }
+    p.total_kb = total_kb;
+    if (d.w_ld < total_kb * IG_BK || (d.w_ld % 8) != 0 || (reinterpret_cast<uintptr_t>(d.w) & 15)) {
+        b2_set_error("igemm(swap): weight ld %d < K %d or misaligned", d.w_ld, total_kb * IG_BK);
+        return -1;
+    }
+    if (encode_w_map(&p.tmB, d.w, d.w_rows, d.w_ld, IG_BM)) return -1;
+    p.a_bytes = IG_BM * IG_BK * 2;            // weight tile (lands in the A region)
+    p.b_bytes = (uint32_t)BN * IG_BK * 2;     // pixel tile
+    int splits = d.splits < 1 ? 1 : d.splits;
+    if (splits > total_kb) splits = total_kb;
+    if (splits >= 8) splits = 8; else if (splits >= 4) splits = 4; else if (splits >= 2) splits = 2;
+    p.kb_per_split = (total_kb + splits - 1) / splits;
+    while (splits > 1 && (total_kb + p.kb_per_split - 1) / p.kb_per_split != splits) {
+        splits >>= 1;
+        p.kb_per_split = (total_kb + splits - 1) / splits;
+    }
+    plan->splits = splits;
+    plan->rows_total = rows_total;
+    p.epi = d.epi;
+    p.dbg_ts = d.dbg_ts;
+    if (splits > 1) p.epi.flags |= IG_SPLITK;
+    const int c_tiles = (d.epi.n_valid + IG_BM - 1) / IG_BM;
+    p.n_pad = c_tiles * IG_BM;
+    const size_t stage_bytes = (size_t)IG_BM * IG_BK * 2 + (size_t)BN * IG_BK * 2;
+    int stages = (int)((100 * 1024) / stage_bytes);
+    if (stages < 2) stages = 2;
+    if (stages > IG_MAX_STAGES) stages = IG_MAX_STAGES;
+    if (stages > p.kb_per_split) stages = p.kb_per_split < 2 ? 2 : p.kb_per_split;
+    size_t pipe_bytes = stages * stage_bytes;
+    if (splits > 1) {
+        const size_t stg = (size_t)BN * IG_BM * 4;
+        if (stg > pipe_bytes) {
+            stages = (int)((stg + stage_bytes - 1) / stage_bytes);
+            if (stages > IG_MAX_STAGES) {
+                b2_set_error("igemm(swap): split-K staging does not fit (BN %d)", BN);
+                return -1;
+            }
+            pipe_bytes = stages * stage_bytes;
+        }
+    }
+    p.num_stages = stages;
+    plan->smem = pipe_bytes + 1024 + 512;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)BN) cols <<= 1;
+    p.tmem_cols = cols;
+    plan->grid = dim3(p.tiles_w * p.tiles_h * p.tiles_n, c_tiles, splits);
+    plan->mode = 0;
+    return 0;
+}
+
 int igemm_plan(const IgemmDesc& d, IgemmPlan* plan) {
     memset(plan, 0, sizeof(*plan));
+    if (d.swap) return plan_swap(d, plan);
     IgemmParams& p = plan->p;
     if (d.nseg < 1 || d.nseg > IG_MAX_SRC) {
         b2_set_error("igemm: bad nseg %d", d.nseg);

@@ -61,6 +61,8 @@ struct IgemmParams {
     float* partial;               // [splits][rows_total][n_pad] fp32 (split-K only)
     int* tile_counters;           // one int per (m tile, n tile), zero between launches (split-K only)
     int n_pad;
+    int swap;                     // 1: weights on the M side (128 output channels per CTA), pixels on the N side
+    int tw_log2, th_log2;         // swap mode: pixel-tile extents are powers of two
     IgEpilogue epi;
 };
 
@@ -108,6 +110,7 @@ struct IgemmDesc {
     int stride;
     int Nb, Ho, Wo;
     int BN;           // 0 = auto
+    int swap;         // 1 = swapped orientation: D^T = W . X^T, BN pixels (64/128/256) on the N side, transposed store
     int splits;       // 0/1 = none
     unsigned long long* dbg_ts;  // optional per-CTA timeline (8 stamps per CTA)
     float* partial;   // workspace for split-K (size splits*rows*n_pad floats)

@@ -28,7 +28,7 @@ class IgemmDesc(C.Structure):
         ("colbias", C.c_void_p), ("colbias_bstride", C.c_int),
         ("res", C.c_void_p), ("ldr", C.c_int),
         ("acc_scale", C.c_float), ("res_scale", C.c_float),
-        ("flags", C.c_int), ("n_valid", C.c_int),
+        ("flags", C.c_int), ("n_valid", C.c_int), ("swap", C.c_int),
     ]
 
 

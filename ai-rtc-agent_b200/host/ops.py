@@ -31,7 +31,7 @@ def _view(t: torch.Tensor) -> capi.ActView:
 def igemm(srcs: Sequence[Tuple[torch.Tensor, int]], w: torch.Tensor, out: torch.Tensor, *,
           stride: int = 1, colbias: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
           acc_scale: float = 1.0, res_scale: float = 1.0, relu: bool = False, geglu: bool = False,
-          bn: int = 0, splits: int = 1, n_valid: Optional[int] = None, timeline: Optional[torch.Tensor] = None) -> torch.Tensor:
+          bn: int = 0, splits: int = 1, n_valid: Optional[int] = None, timeline: Optional[torch.Tensor] = None, swap: bool = False) -> torch.Tensor:
     """srcs: [(NHWC fp16 tensor, ntap)], w: packed fp16 [rows, K]; out: NHWC fp16 [nb,ho,wo,ldc>=n]."""
     d = capi.IgemmDesc()
     d.nseg = len(srcs)
@@ -44,6 +44,7 @@ def igemm(srcs: Sequence[Tuple[torch.Tensor, int]], w: torch.Tensor, out: torch.
     nb, ho, wo, _ = out.shape
     d.nb, d.ho, d.wo = nb, ho, wo
     d.bn, d.splits = bn, splits
+    d.swap = int(swap)
     d.out, d.ldc = out.data_ptr(), out.stride(2)
     nv = n_valid if n_valid is not None else out.shape[3]
     d.n_valid = nv

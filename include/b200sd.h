@@ -63,6 +63,7 @@ typedef struct {
     float acc_scale, res_scale;
     int flags;
     int n_valid;       /* output channels */
+    int swap;          /* 1: swapped orientation (output channels on the MMA M side, bn = 64/128/256 pixels on N) */
 } b2sd_igemm_desc;
 
 int b2sd_op_igemm(const b2sd_igemm_desc* d, void* stream);

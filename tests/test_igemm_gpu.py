@@ -165,3 +165,44 @@ def test_swapped_operands_vt(cuda):
     ops.igemm([(wv, 1)], x, out, bn=128)
     ref = wv.float().reshape(c, c) @ x.float().t()
     assert_close(out.reshape(c, tokens), ref, 2e-3, 2e-3, "V^T swapped-operand GEMM")
+
+
+@pytest.mark.parametrize("nb,h,w,cin,cout,stride,bn,splits,res", [
+    (1, 16, 16, 64, 128, 1, 256, 1, False),    # one pixel tile, one channel tile
+    (1, 64, 64, 320, 320, 1, 256, 2, True),    # UNet 64^2 resnet conv2 (+x), 320 = 2.5 channel tiles
+    (1, 32, 32, 640, 640, 1, 256, 4, False),
+    (1, 16, 16, 1280, 1280, 1, 256, 8, True),
+    (1, 8, 8, 1280, 1280, 1, 64, 8, False),
+    (4, 8, 8, 1280, 1280, 1, 256, 8, False),   # four images in one pixel tile
+    (1, 64, 64, 320, 320, 2, 256, 1, False),   # stride-2 downsample
+    (2, 24, 24, 128, 192, 1, 128, 1, False),   # ragged extents
+])
+def test_conv3x3_swapped_orientation(cuda, nb, h, w, cin, cout, stride, bn, splits, res):
+    """D^T = W . X^T: output channels on the MMA M side, a tile of bn pixels on the N side, transposed store."""
+    ops = _ops()
+    x = _nhwc16(_rand((nb, cin, h, w), cuda, 1))
+    wt = _rand((cout, cin, 3, 3), cuda, 2, 1.0 / math.sqrt(9 * cin)).to(torch.float16)
+    bias = _rand((nb, cout), cuda, 3).float().contiguous()
+    ho, wo = h // stride, w // stride
+    r = _nhwc16(_rand((nb, cout, ho, wo), cuda, 4)) if res else None
+    out = torch.full((nb, ho, wo, cout), float("nan"), dtype=torch.float16, device=cuda)
+    wp = ops.pack_conv_weight(wt)
+    ops.igemm([(x, 9)], wp, out, stride=stride, colbias=bias, res=r, bn=bn, splits=splits, swap=True)
+    ref = _ref_conv(x, wt, stride) + bias[:, None, None, :]
+    if res:
+        ref = ref + r.float()
+    assert_close(out, ref, 4e-3, 3e-3, f"swapped conv nb={nb} {h}x{w} {cin}->{cout} s{stride} bn={bn} splits={splits}")
+
+
+@pytest.mark.parametrize("m,k,n,bn,splits", [(4096, 320, 320, 256, 1), (1024, 640, 640, 256, 2), (256, 1280, 1280, 256, 4),
+                                               (64, 1280, 1280, 64, 8), (77, 1024, 640, 128, 1), (4096, 1280, 320, 256, 4)])
+def test_linear_swapped_orientation(cuda, m, k, n, bn, splits):
+    ops = _ops()
+    x = _rand((1, 1, m, k), cuda, 1).to(torch.float16)
+    w = _rand((n, k), cuda, 2, 1.0 / math.sqrt(k)).to(torch.float16)
+    bias = _rand((1, n), cuda, 3).float().contiguous()
+    res = _rand((1, 1, m, n), cuda, 4).to(torch.float16)
+    out = torch.full((1, 1, m, n), float("nan"), dtype=torch.float16, device=cuda)
+    ops.igemm([(x, 1)], w, out, colbias=bias, res=res, bn=bn, splits=splits, swap=True)
+    ref = x.float().reshape(m, k) @ w.float().t() + bias + res.float().reshape(m, n)
+    assert_close(out.reshape(m, n), ref, 4e-3, 3e-3, f"swapped linear m={m} k={k} n={n}")
