@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                                                ~static_cast<uintptr_t>(1023));
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t stage_bytes = IG_BM * IG_BK * 2 + (uint32_t)p.BN * IG_BK * 2;
+    const uint32_t stage_bytes = (uint32_t)p.kpack * (IG_BM * IG_BK * 2 + (uint32_t)p.BN * IG_BK * 2);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.num_stages * stage_bytes);
     uint64_t* fullb_bar = full_bar + IG_MAX_STAGES;
     uint64_t* empty_bar = fullb_bar + IG_MAX_STAGES;
@@ -294,26 +294,31 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
             int cb = (kb_begin - base) % p.seg_cblocks[seg];
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = kb_begin; kb < kb_end; ++kb) {
+            const uint32_t sub_bytes = IG_BM * IG_BK * 2 + (uint32_t)p.BN * IG_BK * 2;
+            for (int kb = kb_begin; kb < kb_end; kb += p.kpack) {
+                // one pipeline stage = up to `kpack` consecutive k-blocks (one barrier round trip for all of them)
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                uint8_t* sb = sa + IG_BM * IG_BK * 2;
-                mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
-                int dy = 0, dx = 0;
-                if (p.seg_ntap[seg] == 9) {
-                    dy = tap / 3 - 1;
-                    dx = tap % 3 - 1;
-                }
-                // normal: pixels -> A (M side), weights -> B.  swapped: weights (128 output channels) -> A, pixels -> B
-                tma_load_4d(p.swap ? sb : sa, &p.tmA[seg], &full_bar[stage], p.seg_c0[seg] + cb * IG_BK,
-                            w0 * p.stride + dx, h0 * p.stride + dy, n0);
-                tma_load_2d(p.swap ? sa : sb, &p.tmB, &full_bar[stage], kb * IG_BK, ntile * (p.swap ? IG_BM : p.BN));
-                if (ts && kb == kb_begin) ts[2] = globaltimer_ns();
-                if (++cb == p.seg_cblocks[seg]) {
-                    cb = 0;
-                    if (++tap == p.seg_ntap[seg]) {
-                        tap = 0;
-                        ++seg;
+                const int nsub = min(p.kpack, kb_end - kb);
+                mbar_expect_tx(&full_bar[stage], (uint32_t)nsub * (p.a_bytes + p.b_bytes));
+                for (int sub = 0; sub < nsub; ++sub) {
+                    uint8_t* sa = smem + (size_t)stage * stage_bytes + (size_t)sub * sub_bytes;
+                    uint8_t* sb = sa + IG_BM * IG_BK * 2;
+                    int dy = 0, dx = 0;
+                    if (p.seg_ntap[seg] == 9) {
+                        dy = tap / 3 - 1;
+                        dx = tap % 3 - 1;
+                    }
+                    // normal: pixels -> A (M side), weights -> B.  swapped: weights (128 output channels) -> A, pixels -> B
+                    tma_load_4d(p.swap ? sb : sa, &p.tmA[seg], &full_bar[stage], p.seg_c0[seg] + cb * IG_BK,
+                                w0 * p.stride + dx, h0 * p.stride + dy, n0);
+                    tma_load_2d(p.swap ? sa : sb, &p.tmB, &full_bar[stage], (kb + sub) * IG_BK, ntile * (p.swap ? IG_BM : p.BN));
+                    if (ts && kb == kb_begin && sub == 0) ts[2] = globaltimer_ns();
+                    if (++cb == p.seg_cblocks[seg]) {
+                        cb = 0;
+                        if (++tap == p.seg_ntap[seg]) {
+                            tap = 0;
+                            ++seg;
+                        }
                     }
                 }
                 if (++stage == p.num_stages) {
@@ -331,20 +336,24 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
         const uint32_t smem_base = smem_u32(smem);
         int stage = 0;
         uint32_t phase = 0;
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const uint32_t sub_bytes = IG_BM * IG_BK * 2 + (uint32_t)p.BN * IG_BK * 2;
+        for (int kb = kb_begin; kb < kb_end; kb += p.kpack) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             if (ts && kb == kb_begin && lane == 0) ts[3] = globaltimer_ns();
-            const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-            const uint64_t da = make_kmajor_sw128_desc(sa);
-            const uint64_t db = make_kmajor_sw128_desc(sa + IG_BM * IG_BK * 2);
-            const uint32_t acc0 = kb > kb_begin ? 1u : 0u;
+            const int nsub = min(p.kpack, kb_end - kb);
+            const uint32_t sa0 = smem_base + (uint32_t)stage * stage_bytes;
             if (elect_one()) {
-                // +32 B per UMMA_K inside the 128 B swizzle row => +2 in the (addr>>4) field
-                umma_f16(tmem_base, da, db, idesc, acc0);
-                umma_f16(tmem_base, da + 2, db + 2, idesc, 1u);
-                umma_f16(tmem_base, da + 4, db + 4, idesc, 1u);
-                umma_f16(tmem_base, da + 6, db + 6, idesc, 1u);
+                for (int sub = 0; sub < nsub; ++sub) {
+                    const uint32_t sa = sa0 + (uint32_t)sub * sub_bytes;
+                    const uint64_t da = make_kmajor_sw128_desc(sa);
+                    const uint64_t db = make_kmajor_sw128_desc(sa + IG_BM * IG_BK * 2);
+                    // +32 B per UMMA_K inside the 128 B swizzle row => +2 in the (addr>>4) field
+                    umma_f16(tmem_base, da, db, idesc, (kb > kb_begin || sub > 0) ? 1u : 0u);
+                    umma_f16(tmem_base, da + 2, db + 2, idesc, 1u);
+                    umma_f16(tmem_base, da + 4, db + 4, idesc, 1u);
+                    umma_f16(tmem_base, da + 6, db + 6, idesc, 1u);
+                }
                 umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
             }
             __syncwarp();
@@ -907,6 +916,7 @@ static int plan_swap(const IgemmDesc& d, IgemmPlan* plan) {
         return -1;
     }
     p.swap = 1;
+    p.kpack = 1;
     p.BN = BN;
     auto lg = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
     int tw, th, tn;
@@ -1095,7 +1105,13 @@ int igemm_plan(const IgemmDesc& d, IgemmPlan* plan) {
         p.epi.flags |= IG_SPLITK;
     }
     // ---- pipeline depth / smem
-    const size_t stage_bytes = (size_t)IG_BM * IG_BK * 2 + (size_t)BN * IG_BK * 2;
+    static const char* kpack_env = getenv("B2_KPACK");
+    int kpack = kpack_env ? atoi(kpack_env) : 1;  // packing 2+ k-blocks per stage halves the prefetch depth and measured slower
+    if (kpack < 1) kpack = 1;
+    if (kpack > 4) kpack = 4;
+    while (kpack > 1 && p.kb_per_split < 2 * kpack) kpack >>= 1;
+    p.kpack = kpack;
+    const size_t stage_bytes = (size_t)kpack * ((size_t)IG_BM * IG_BK * 2 + (size_t)BN * IG_BK * 2);
     // TMA latency under load is ~1.3 us (tools/timeline.py): throughput per SM = bytes in flight / latency.  With at
     // most ~1 CTA per SM take the whole shared memory for the ring; with many CTAs keep two co-resident instead.
     const long total_ctas = (long)p.tiles_w * p.tiles_h * p.tiles_n * n_tiles * splits;
@@ -1104,7 +1120,7 @@ int igemm_plan(const IgemmDesc& d, IgemmPlan* plan) {
     int stages = (int)(ring_budget / stage_bytes);
     if (stages < 2) stages = 2;
     if (stages > IG_MAX_STAGES) stages = IG_MAX_STAGES;
-    if (stages > p.kb_per_split) stages = p.kb_per_split < 2 ? 2 : p.kb_per_split;
+    if (stages > (p.kb_per_split + kpack - 1) / kpack) stages = (p.kb_per_split + kpack - 1) / kpack < 2 ? 2 : (p.kb_per_split + kpack - 1) / kpack;
     p.num_stages = stages;
     size_t pipe_bytes = stages * stage_bytes;
     if (splits > 1) {
