@@ -23,12 +23,32 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# workload table: BASELINE.json configs[1] is the default (the configuration the headline metric is quoted on);
+# the others are the remaining single-GPU configs, selectable for additional measurements (--workload)
+WORKLOADS = {
+    "sd-turbo-512": dict(model="stabilityai/sd-turbo", t=[32], hw=512, gflop=1068.0,
+                         metric="frames/sec at 512x512 SD-Turbo img2img (1-step, stream-batch 1)",
+                         name="SD-Turbo 1-step img2img 512x512, stream-batch=1, synthetic RGB frame feed (BASELINE.json configs[1])"),
+    "sd15-lcm4-512": dict(model="lykon/dreamshaper-8", t=[18, 26, 35, 45], hw=512, gflop=3476.9,
+                          metric="frames/sec at 512x512 SD-1.5 + LCM 4-step img2img (stream-batch 4)",
+                          name="SD-1.5 + LCM-LoRA 4-step img2img 512x512, stream-batch=4 (BASELINE.json configs[2])"),
+    "sd15-lcm4-768": dict(model="lykon/dreamshaper-8", t=[18, 26, 35, 45], hw=768, gflop=9185.6,
+                          metric="frames/sec at 768x768 SD-1.5 + LCM 4-step img2img (stream-batch 4)",
+                          name="SD-1.5 + LCM-LoRA 4-step img2img 768x768, stream-batch=4, synthetic feed (BASELINE.json configs[4] without codecs)"),
+}
 MODEL_ID = "stabilityai/sd-turbo"
 T_INDEX_LIST = [32]
 H = W = 512
-METRIC = "frames/sec at 512x512 SD-Turbo img2img (1-step, stream-batch 1)"
+METRIC = WORKLOADS["sd-turbo-512"]["metric"]
 GFLOP_PER_FRAME = 1068.0  # 804.3 (UNet) + 122.3 (TAESD enc) + 141.4 (TAESD dec)
-WORKLOAD = "SD-Turbo 1-step img2img 512x512, stream-batch=1, synthetic RGB frame feed (BASELINE.json configs[1])"
+WORKLOAD = WORKLOADS["sd-turbo-512"]["name"]
+
+
+def select_workload(key: str) -> None:
+    global MODEL_ID, T_INDEX_LIST, H, W, METRIC, GFLOP_PER_FRAME, WORKLOAD
+    w = WORKLOADS[key]
+    MODEL_ID, T_INDEX_LIST, METRIC, GFLOP_PER_FRAME, WORKLOAD = w["model"], w["t"], w["metric"], w["gflop"], w["name"]
+    H = W = w["hw"]
 
 
 def measured_peaks():
@@ -98,7 +118,7 @@ def run_oracle(steps: int, warmup: int, budget_s: float):
     from oracle import unet as ounet
     from oracle import weights as ow
     threads = torch.get_num_threads()   # torch's default = physical cores; oversubscribing the SMT siblings is slower
-    cfg = ounet.SD_TURBO
+    cfg = ounet.config_for(MODEL_ID)
     usd = ow.to_float(ow.make_unet_weights(cfg))
     vsd = ow.to_float(ow.make_taesd_weights())
     orc = ostream.StreamOracle(usd, cfg, vsd, T_INDEX_LIST, W, H)
@@ -148,6 +168,7 @@ def main_gpu(args):
     import torch
     import torch.distributed as dist
     os.environ.setdefault("B200SD_SYNTHETIC_WEIGHTS", "1")
+    os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line (NCCL prints its version banner otherwise)
     os.environ["NVENC"] = "1"  # keep the output tensor in HBM (lib/pipeline.py:83,96)
     from ai_rtc_agent_b200.host import dist as bdist
     from ai_rtc_agent_b200.host.pipeline import StreamDiffusionPipeline
@@ -257,7 +278,8 @@ def main_gpu(args):
         "dtype": "f16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "t_index_list": T_INDEX_LIST, "weights": "seeded synthetic (no checkpoint offline)",
                    "parallelism": f"dp{world}: one independent stream per GPU, NCCL weight broadcast at init only",
-                   "l2": "UNet weights (1.73 GB) are re-streamed from HBM every step (>> 126 MB L2); 64-frame input ring"},
+                   "l2": "UNet weights (1.73 GB) are re-streamed from HBM every step (>> 126 MB L2); 64-frame input ring",
+                   "model": MODEL_ID},
         "p50_ms": p50.item(),
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": H * W * 3, "d2h_bytes_per_step": H * W * 3,
                 "p50_ms": p50.item()},
@@ -278,5 +300,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="sd-turbo-512", choices=sorted(WORKLOADS))
     a = ap.parse_args()
+    select_workload(a.workload)
     sys.exit(main_reference(a) if a.impl == "reference" else main_gpu(a))
