@@ -116,47 +116,50 @@ __global__ void __launch_bounds__(AT_THREADS) attn_kernel(const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            const uint32_t idesc_s = make_idesc_f16(AT_BQ, BKV);
-            const uint32_t idesc_o = make_idesc_f16(AT_BQ, DP);
-            auto issue_qk = [&](int j) {
-                const int st = j % AT_STAGES;
-                mbar_wait(&kv_full[st], (j / AT_STAGES) & 1);
-                mbar_wait(s_empty, (j & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t sk = smem_u32(sKV + st * STAGE_BYTES);
-                const uint32_t tS = tmem_base;
+        // ===== MMA issuer: the whole warp walks the loop (uniform control flow => descriptors stay in uniform
+        // registers), one elected lane issues (see igemm.cu) =====
+        const uint32_t idesc_s = make_idesc_f16(AT_BQ, BKV);
+        const uint32_t idesc_o = make_idesc_f16(AT_BQ, DP);
+        const uint32_t sq_addr = smem_u32(sQ), skv_addr = smem_u32(sKV), sp_addr = smem_u32(sP);
+        auto issue_qk = [&](int j) {
+            const int st = j % AT_STAGES;
+            mbar_wait(&kv_full[st], (j / AT_STAGES) & 1);
+            mbar_wait(s_empty, (j & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t sk = skv_addr + st * STAGE_BYTES;
+            if (elect_one()) {
 #pragma unroll
                 for (int a = 0; a < DA; ++a) {
-                    const uint64_t dq = make_kmajor_sw128_desc(smem_u32(sQ) + a * (AT_BQ * 128));
+                    const uint64_t dq = make_kmajor_sw128_desc(sq_addr + a * (AT_BQ * 128));
                     const uint64_t dk = make_kmajor_sw128_desc(sk + a * (BKV * 128));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_f16(tS, dq + 2 * k, dk + 2 * k, idesc_s, (a | k) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) umma_f16(tmem_base, dq + 2 * k, dk + 2 * k, idesc_s, (a | k) ? 1u : 0u);
                 }
                 umma_commit(s_full);
-            };
-            mbar_wait(q_full, 0);
-            issue_qk(0);
-            for (int j = 0; j < nblk; ++j) {
-                if (j + 1 < nblk) issue_qk(j + 1);  // issues as soon as softmax(j) has drained S; overlaps its P stores
-                const int st = j % AT_STAGES;
-                mbar_wait(p_full, j & 1);
-                tc_fence_after();
-                const uint32_t sv = smem_u32(sKV + st * STAGE_BYTES + K_BYTES);
+            }
+            __syncwarp();
+        };
+        mbar_wait(q_full, 0);
+        issue_qk(0);
+        for (int j = 0; j < nblk; ++j) {
+            if (j + 1 < nblk) issue_qk(j + 1);  // issues as soon as softmax(j) has drained S; overlaps its P stores
+            const int st = j % AT_STAGES;
+            mbar_wait(p_full, j & 1);
+            tc_fence_after();
+            const uint32_t sv = skv_addr + st * STAGE_BYTES + K_BYTES;
+            if (elect_one()) {
 #pragma unroll
                 for (int a = 0; a < KVA; ++a) {
-                    const uint64_t dp = make_kmajor_sw128_desc(smem_u32(sP) + a * (AT_BQ * 128));
+                    const uint64_t dp = make_kmajor_sw128_desc(sp_addr + a * (AT_BQ * 128));
                     const uint64_t dv = make_kmajor_sw128_desc(sv + a * (DP * 128));
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_f16(tmem_base + BKV, dp + 2 * k, dv + 2 * k, idesc_o,
-                                 (j > 0 || a > 0 || k > 0) ? 1u : 0u);
+                        umma_f16(tmem_base + BKV, dp + 2 * k, dv + 2 * k, idesc_o, (j > 0 || a > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(o_done);
                 umma_commit(&kv_empty[st]);
             }
+            __syncwarp();
         }
     } else {
         // ===== softmax / correction / epilogue: thread owns query row r =====

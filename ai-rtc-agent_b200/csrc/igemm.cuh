@@ -54,6 +54,7 @@ struct IgemmParams {
     int stride;                   // input coord = stride * out + tap - 1
     int BN;                       // UMMA N (multiple of 16, <= 256)
     int num_stages;
+    int acc_bufs;                 // 1, or 2 when the launch is persistent over M tiles (double-buffered accumulator)
     int kpack;                    // k-blocks per pipeline stage (one mbarrier round trip covers all of them)
     uint32_t a_bytes;             // TMA box bytes of one A tile
     uint32_t b_bytes;

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ Prob
         const uint32_t idesc = make_idesc_f16(128, 64);
         for (int k = 0; k < 4; ++k) umma_f16(tmem, da + 2 * k, db + 2 * k, idesc, k > 0);
         umma_commit(mma_bar);
-        if (p.timing && !(p.base_mode & 128)) {
+        if (p.timing && !(p.base_mode & (128 | 256))) {
             // (A) divergent single-thread issue: loop runs under `if (threadIdx.x == 0)`
             mbar_wait(mma_bar, 0);
             const long long c0 = clock64();
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ Prob
             *reinterpret_cast<volatile uint32_t*>(slot + 1) = 1;  // release the spinners
         }
     }
-    if (p.timing && (p.base_mode & 128) && warp == 0) {
+    if (p.timing && (p.base_mode & 128) && !(p.base_mode & 256) && warp == 0) {
         // (B) warp-uniform issue: every lane of warp 0 runs the loop, one elected lane issues -> operands can live in
         // uniform registers
         mbar_wait(mma_bar, 0);
@@ -120,6 +120,42 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ Prob
         }
         if (lane == 0) *reinterpret_cast<volatile uint32_t*>(slot + 1) = 1;
     }
+    if (p.timing && (p.base_mode & 256) && warp == 0) {
+        // (C) warp-uniform issue with the stage loop unrolled by 4: all descriptors are loop-invariant per unrolled slot
+        mbar_wait(mma_bar, 0);
+        const uint32_t idesc = make_idesc_f16(128, 64);
+        uint64_t da[4], db[4];
+#pragma unroll
+        for (int st = 0; st < 4; ++st) {
+            da[st] = make_kmajor_sw128_desc(smem_u32(sA) + st * 8192);   // four "stages" inside the loaded tile
+            db[st] = make_kmajor_sw128_desc(smem_u32(sB));
+        }
+        const long long c0 = clock64();
+        const unsigned long long g0 = globaltimer_ns();
+        for (int it = 0; it < 64; ++it) {
+#pragma unroll
+            for (int st = 0; st < 4; ++st) {
+                if (p.base_mode & 32) mbar_wait(mma_bar, 0);
+                if (p.base_mode & 16) tc_fence_after();
+                if (elect_one()) {
+                    umma_f16(tmem, da[st], db[st], idesc, 1);
+                    umma_f16(tmem, da[st] + 2, db[st] + 2, idesc, 1);
+                    umma_f16(tmem, da[st] + 4, db[st] + 4, idesc, 1);
+                    umma_f16(tmem, da[st] + 6, db[st] + 6, idesc, 1);
+                    if (p.base_mode & 4) umma_commit(mma_bar + 2);
+                }
+                __syncwarp();
+            }
+        }
+        if (elect_one()) umma_commit(bar);
+        __syncwarp();
+        mbar_wait(bar, 1);
+        if (blockIdx.x == 0 && lane == 0) {
+            p.timing[0] = clock64() - c0;
+            p.timing[1] = (long long)(globaltimer_ns() - g0);
+        }
+        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(slot + 1) = 1;
+    }
     if (p.timing && (p.base_mode & 2) && threadIdx.x >= 32) {
         // like the epilogue warps of the real kernels: wait on an mbarrier that completes only at the very end
         while (*reinterpret_cast<volatile uint32_t*>(slot + 1) == 0) mbar_try_wait(mma_bar + 3, 0);
@@ -132,7 +168,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ Prob
             mbar_wait(mma_bar + 4, it & 1);
         }
     }
-    if (!(p.timing && (threadIdx.x == 0 || ((p.base_mode & 128) && warp == 0)))) mbar_wait(mma_bar, 0);
+    if (!(p.timing && (threadIdx.x == 0 || ((p.base_mode & (128 | 256)) && warp == 0)))) mbar_wait(mma_bar, 0);
     __syncthreads();
     tc_fence_after();
     const int r = warp * 32 + lane;

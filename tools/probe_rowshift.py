@@ -9,7 +9,7 @@ torch.manual_seed(0)
 rows = 256
 A = torch.randn(rows, 64, device=dev).half(); B = torch.randn(64, 64, device=dev).half()
 tm = torch.zeros(2, dtype=torch.int64, device=dev)
-for mode, what in [(0, "divergent issue, plain"), (48, "divergent issue, wait+fence per 4 MMAs"), (128, "uniform issue, plain"), (176, "uniform issue, wait+fence per 4 MMAs"), (244, "uniform, wait+fence+commit+alt accum")]:
+for mode, what in [(128, "uniform issue, plain"), (176, "uniform, wait+fence per 4 MMAs"), (256+128, "unrolled x4, plain"), (256+128+48, "unrolled x4, wait+fence"), (256+128+48+4, "unrolled x4, wait+fence+commit")]:
     D = torch.zeros(128, 64, device=dev)
     lib.b2sd_probe_umma_rowshift(A.data_ptr(), rows, B.data_ptr(), D.data_ptr(), 0, 8, mode, torch.cuda.current_stream().cuda_stream, tm.data_ptr())
     torch.cuda.synchronize()
