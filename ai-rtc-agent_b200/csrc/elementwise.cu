@@ -101,49 +101,60 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(GroupNormArgs a, int ppc,
     __syncthreads();
     // reduce over pixel rows, then over the channels of each group
     const int cpg = C / a.groups;
-    for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
-        float gs = 0.f, gq = 0.f;
-        for (int c = g * cpg; c < (g + 1) * cpg; ++c)
-            for (int r = 0; r < rpi; ++r) {
+    {
+        // 8 lanes per group: lane `part` sums entries part, part+8, ... of the group's cpg*rpi (channel,row) pairs, then a
+        // fixed 3-step shuffle tree combines the 8 parts
+        const int part = threadIdx.x & 7;
+        const int nent = cpg * rpi;
+        for (int g = threadIdx.x >> 3; g < a.groups; g += blockDim.x >> 3) {
+            float gs = 0.f, gq = 0.f;
+            for (int e = part; e < nent; e += 8) {
+                const int c = g * cpg + e % cpg, r = e / cpg;
                 gs += sm[((long)r * C + c) * 2];
                 gq += sm[((long)r * C + c) * 2 + 1];
             }
-        float* dst = a.partial + (((long)b * GN_MAX_CHUNKS + chunk) * a.groups + g) * 2;
-        dst[0] = gs;
-        dst[1] = gq;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+                gs += __shfl_xor_sync(0xffffffffu, gs, o);
+                gq += __shfl_xor_sync(0xffffffffu, gq, o);
+            }
+            if (part == 0)
+                reinterpret_cast<float2*>(a.partial)[((long)b * a.groups + g) * GN_MAX_CHUNKS + chunk] = make_float2(gs, gq);
+        }
     }
 }
 
-// mean / rstd of every group of batch item b from the per-chunk partial sums, computed by the whole CTA in a
-// fixed order (thread (slice, g) sums chunks slice, slice+S, ...; then thread g sums the S slices).
-__device__ __forceinline__ void gn_finalize_stats(const GroupNormArgs& a, int b, int nchunks, float* scratch /*[S][G][2]*/,
+// mean / rstd of every group of batch item b from the per-chunk partial sums (layout [b][group][chunk]): one warp
+// per group reads the chunk partials with coalesced loads (all in flight at once) and reduces them with a fixed
+// shuffle tree, so the result is deterministic and costs about one L2 round trip.
+__device__ __forceinline__ void gn_finalize_stats(const GroupNormArgs& a, int b, int nchunks, float* /*scratch*/,
                                                   float* s_mean, float* s_rstd) {
     const int G = a.groups;
-    const int S = min(16, (int)blockDim.x / G);
-    const int g = threadIdx.x % G, slice = threadIdx.x / G;
-    if (slice < S) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = (blockDim.x + 31) >> 5;
+    const int cpg = (a.ca + a.cb) / G;
+    const float inv_n = 1.0f / ((float)a.hw * (float)cpg);
+    for (int g = warp; g < G; g += nwarps) {
+        const float2* src = reinterpret_cast<const float2*>(a.partial) + ((long)b * G + g) * GN_MAX_CHUNKS;
+        float2 v[GN_MAX_CHUNKS / 32];
+#pragma unroll
+        for (int k = 0; k < GN_MAX_CHUNKS / 32; ++k)
+            v[k] = (lane + 32 * k < nchunks) ? __ldcg(src + lane + 32 * k) : make_float2(0.f, 0.f);
         float gs = 0.f, gq = 0.f;
-        const float* src = a.partial + ((long)b * GN_MAX_CHUNKS * G + g) * 2;
-        for (int k = slice; k < nchunks; k += S) {
-            const float2 v = __ldcg(reinterpret_cast<const float2*>(src + (long)k * G * 2));
-            gs += v.x;
-            gq += v.y;
+#pragma unroll
+        for (int k = 0; k < GN_MAX_CHUNKS / 32; ++k) {
+            gs += v[k].x;
+            gq += v[k].y;
         }
-        scratch[(slice * G + g) * 2] = gs;
-        scratch[(slice * G + g) * 2 + 1] = gq;
-    }
-    __syncthreads();
-    if (threadIdx.x < G) {
-        float gs = 0.f, gq = 0.f;
-        for (int k = 0; k < S; ++k) {
-            gs += scratch[(k * G + threadIdx.x) * 2];
-            gq += scratch[(k * G + threadIdx.x) * 2 + 1];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            gs += __shfl_xor_sync(0xffffffffu, gs, o);
+            gq += __shfl_xor_sync(0xffffffffu, gq, o);
         }
-        const int cpg = (a.ca + a.cb) / G;
-        const float inv_n = 1.0f / ((float)a.hw * (float)cpg);
-        const float mean = gs * inv_n;
-        s_mean[threadIdx.x] = mean;
-        s_rstd[threadIdx.x] = rsqrtf(fmaxf(gq * inv_n - mean * mean, 0.f) + a.eps);
+        if (lane == 0) {
+            const float mean = gs * inv_n;
+            s_mean[g] = mean;
+            s_rstd[g] = rsqrtf(fmaxf(gq * inv_n - mean * mean, 0.f) + a.eps);
+        }
     }
     __syncthreads();
 }
@@ -240,17 +251,32 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(GroupNormArgs a, int ppc,
     }
     __syncthreads();
     const int cpg = C / a.groups;
-    for (int g = threadIdx.x; g < a.groups; g += blockDim.x) {
-        float gs = 0.f, gq = 0.f;
-        for (int c = g * cpg; c < (g + 1) * cpg; ++c)
-            for (int r = 0; r < rpi; ++r) {
+    {
+        // 8 lanes per group: lane `part` sums entries part, part+8, ... of the group's cpg*rpi (channel,row) pairs, then a
+        // fixed 3-step shuffle tree combines the 8 parts
+        const int part = threadIdx.x & 7;
+        const int nent = cpg * rpi;
+        for (int g = threadIdx.x >> 3; g < a.groups; g += blockDim.x >> 3) {
+            float gs = 0.f, gq = 0.f;
+            for (int e = part; e < nent; e += 8) {
+                const int c = g * cpg + e % cpg, r = e / cpg;
                 gs += sm[((long)r * C + c) * 2];
                 gq += sm[((long)r * C + c) * 2 + 1];
             }
-        float* dst = a.partial + (((long)b * GN_MAX_CHUNKS + chunk) * a.groups + g) * 2;
-        dst[0] = gs;
-        dst[1] = gq;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+                gs += __shfl_xor_sync(0xffffffffu, gs, o);
+                gq += __shfl_xor_sync(0xffffffffu, gq, o);
+            }
+            if (part == 0)
+                reinterpret_cast<float2*>(a.partial)[((long)b * a.groups + g) * GN_MAX_CHUNKS + chunk] = make_float2(gs, gq);
+        }
     }
+    // affine parameters: fetched now so their latency hides behind the grid barrier
+    const float4 g0 = *reinterpret_cast<const float4*>(a.gamma + c0);
+    const float4 g1 = *reinterpret_cast<const float4*>(a.gamma + c0 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(a.beta + c0);
+    const float4 b1 = *reinterpret_cast<const float4*>(a.beta + c0 + 4);
     // ---- barrier over the CTAs of this batch item
     __threadfence();
     __syncthreads();
@@ -278,10 +304,6 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(GroupNormArgs a, int ppc,
     __syncthreads();
     gn_finalize_stats(a, b, nchunks, sm, s_mean, s_rstd);  // sm (>= 16*G*2 floats) is free again
     if (prow < rpi) {
-        const float4 g0 = *reinterpret_cast<const float4*>(a.gamma + c0);
-        const float4 g1 = *reinterpret_cast<const float4*>(a.gamma + c0 + 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(a.beta + c0);
-        const float4 b1 = *reinterpret_cast<const float4*>(a.beta + c0 + 4);
         const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
         const float bet[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         float mu[8], rs[8];
@@ -488,23 +510,19 @@ int smallconv_prep_launch(const __half* w_oihw, float* wt, int cout, int cin, cu
 template <int CIN>
 __global__ void __launch_bounds__(128) smallconv_kernel(SmallConvArgs a) {
     B2_PDL_ENTRY();
-    extern __shared__ float ws[];  // [CIN*9][cout] then bias[cout]
+    extern __shared__ float ws[];  // [CIN*9][64] weights of this CTA's channel group, then bias[64]
     constexpr int K = CIN * 9;
     const int cout = a.cout;
-    {
-        const float4* src = reinterpret_cast<const float4*>(a.wt);
-        float4* dst = reinterpret_cast<float4*>(ws);
-        for (int i = threadIdx.x; i < K * cout / 4; i += blockDim.x) dst[i] = src[i];
+    const int cg = blockIdx.y;   // 64-channel output group
+    for (int i = threadIdx.x; i < K * 16; i += blockDim.x) {
+        const int k = i >> 4, j = i & 15;
+        reinterpret_cast<float4*>(ws)[i] = *reinterpret_cast<const float4*>(a.wt + (long)k * cout + cg * 64 + 4 * j);
     }
-    float* bs = ws + K * cout;
-    for (int i = threadIdx.x; i < cout; i += blockDim.x) bs[i] = a.bias ? a.bias[i] : 0.f;
+    float* bs = ws + K * 64;
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) bs[i] = a.bias ? a.bias[cg * 64 + i] : 0.f;
     __syncthreads();
-    const int groups = cout >> 6;
     const long npix = (long)a.nb * a.h * a.w_;
-    const long total = npix * groups;
-    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-        const int cg = (int)(e / npix);  // consecutive threads = consecutive pixels of the same channel group
-        const long p = e % npix;
+    for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long)gridDim.x * blockDim.x) {
         const int xw = (int)(p % a.w_);
         const int yh = (int)((p / a.w_) % a.h);
         const int n = (int)(p / ((long)a.w_ * a.h));
@@ -541,16 +559,14 @@ __global__ void __launch_bounds__(128) smallconv_kernel(SmallConvArgs a) {
             }
         }
         float acc[64];
-        const float* bsg = bs + cg * 64;
 #pragma unroll
-        for (int o = 0; o < 64; ++o) acc[o] = bsg[o];
-        const float* wg = ws + cg * 64;
+        for (int o = 0; o < 64; ++o) acc[o] = bs[o];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const float v = patch[k];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const float4 w4 = *reinterpret_cast<const float4*>(wg + k * cout + 4 * j);
+                const float4 w4 = *reinterpret_cast<const float4*>(ws + k * 64 + 4 * j);
                 acc[4 * j] += v * w4.x; acc[4 * j + 1] += v * w4.y; acc[4 * j + 2] += v * w4.z; acc[4 * j + 3] += v * w4.w;
             }
         }
@@ -578,18 +594,20 @@ int smallconv_launch(const SmallConvArgs& a, cudaStream_t s) {
         b2_set_error("smallconv: cin %d cout %d unsupported (cout must be a multiple of 64; prepared weights required)", a.cin, a.cout);
         return -1;
     }
-    const size_t smem = ((size_t)a.cin * 9 * a.cout + a.cout) * sizeof(float);
-    const long total = (long)a.nb * a.h * a.w_ * (a.cout / 64);
-    long blocks = (total + 127) / 128;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    const size_t smem = ((size_t)a.cin * 9 * 64 + 64) * sizeof(float);
+    const int groups = a.cout / 64;
+    const long npix = (long)a.nb * a.h * a.w_;
+    long blocks = (npix + 127) / 128;
+    const long cap = (148 * 8 + groups - 1) / groups;
+    if (blocks > cap) blocks = cap;
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(smallconv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         cudaFuncSetAttribute(smallconv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         attr = true;
     }
-    if (a.cin == 3) B2_LAUNCHED("smallconv", launch_k(smallconv_kernel<3>, dim3((unsigned)blocks), dim3(128), smem, s, 1, a));
-    else B2_LAUNCHED("smallconv", launch_k(smallconv_kernel<4>, dim3((unsigned)blocks), dim3(128), smem, s, 1, a));
+    if (a.cin == 3) B2_LAUNCHED("smallconv", launch_k(smallconv_kernel<3>, dim3((unsigned)blocks, groups), dim3(128), smem, s, 1, a));
+    else B2_LAUNCHED("smallconv", launch_k(smallconv_kernel<4>, dim3((unsigned)blocks, groups), dim3(128), smem, s, 1, a));
     return 0;
 }
 
