@@ -5,6 +5,7 @@
 
 #include "igemm.cuh"  // b2_set_error
 #include "launch.cuh"
+#include "ptx.cuh"
 
 namespace b2 {
 
@@ -339,6 +340,103 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(GroupNormArgs a, int ppc,
 
 static thread_local int g_gn_last_launches = 0;
 int groupnorm_last_launch_count() { return g_gn_last_launches; }
+// ---- cluster variant (default when it fits): one thread-block cluster per (batch item, group).  The group's
+// cpg = C/groups channels are a contiguous 2*cpg-byte run per pixel; the pixels are split over the 1/2/4/8 CTAs of the
+// cluster, every thread keeps its <= 32 half2 words in registers, the (sum, sumsq) pairs of the CTAs are pushed into
+// every peer's shared memory, one cluster barrier, then each CTA normalises straight from registers.  No grid barrier,
+// no workspace, an ordinary (PDL-capable) launch: ~3x shorter than the cooperative whole-grid kernel at batch 1,
+// where GroupNorm is pure latency (61 launches per SD-Turbo frame).
+constexpr int GNC_THREADS = 240;   // a multiple of cpg/2 for cpg in {10, 20, 30, 40, 60, 80}: a thread owns one channel pair
+constexpr int GNC_ITEMS = 32;
+__global__ void __launch_bounds__(GNC_THREADS, 2) gn_cluster_kernel(GroupNormArgs a, int ppc) {
+    __shared__ float2 part[8];   // (sum, sumsq) of every CTA of the cluster, pushed by its owner
+    __shared__ float2 red[8];
+    const int g = blockIdx.x, b = blockIdx.y, rank = blockIdx.z, nrank = gridDim.z;
+    const int C = a.ca + a.cb, cpg = C / a.groups, wpp = cpg >> 1;
+    const int t = threadIdx.x;
+    const int wq = t % wpp, prow = t / wpp, pstep = GNC_THREADS / wpp;
+    const int c = g * cpg + 2 * wq;
+    const bool from_a = c < a.ca;
+    const __half* src = from_a ? a.xa + c : a.xb + (c - a.ca);
+    const int ld = from_a ? a.lda : a.ldb;
+    const float2 gm = *reinterpret_cast<const float2*>(a.gamma + c);   // parameters: not produced by the previous kernel
+    const float2 bt = *reinterpret_cast<const float2*>(a.beta + c);
+    B2_PDL_ENTRY();
+    const int p0 = rank * ppc, p1 = min(a.hw, p0 + ppc);
+    const long rowbase = (long)b * a.hw;
+    uint32_t v[GNC_ITEMS];
+#pragma unroll
+    for (int k = 0; k < GNC_ITEMS; ++k) {
+        const int p = p0 + prow + k * pstep;
+        v[k] = 0u;
+        if (p < p1) v[k] = *reinterpret_cast<const uint32_t*>(src + (rowbase + p) * ld);
+    }
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int k = 0; k < GNC_ITEMS; ++k) {   // out-of-range items are zero: they add nothing
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v[k]));
+        s += f.x + f.y;
+        q += f.x * f.x + f.y * f.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if ((t & 31) == 0) red[t >> 5] = make_float2(s, q);
+    __syncthreads();
+    if (t == 0) {
+        float2 tot = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int w = 0; w < (GNC_THREADS + 31) / 32; ++w) { tot.x += red[w].x; tot.y += red[w].y; }
+        if (nrank == 1) part[0] = tot;
+        else {
+            const uint32_t slot = smem_u32(&part[rank]);
+            for (int r = 0; r < nrank; ++r) dsmem_st_f2(dsmem_map(slot, (uint32_t)r), tot.x, tot.y);
+        }
+    }
+    if (nrank > 1) cluster_sync_all();   // release/acquire over the cluster: every peer's pair has landed
+    else __syncthreads();
+    float S = 0.f, Q = 0.f;
+    for (int r = 0; r < nrank; ++r) { S += part[r].x; Q += part[r].y; }   // fixed order => deterministic
+    const float inv_n = 1.0f / ((float)a.hw * (float)cpg);
+    const float mean = S * inv_n;
+    const float rstd = rsqrtf(fmaxf(Q * inv_n - mean * mean, 0.f) + a.eps);
+    const float ax = rstd * gm.x, ay = rstd * gm.y;
+    const float bx = bt.x - mean * ax, by = bt.y - mean * ay;
+    __half* dst = a.y + c;
+#pragma unroll
+    for (int k = 0; k < GNC_ITEMS; ++k) {
+        const int p = p0 + prow + k * pstep;
+        if (p < p1) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v[k]));
+            float y0 = f.x * ax + bx, y1 = f.y * ay + by;
+            if (a.silu) {
+                y0 = y0 / (1.0f + __expf(-y0));
+                y1 = y1 / (1.0f + __expf(-y1));
+            }
+            *reinterpret_cast<__half2*>(dst + (rowbase + p) * a.ldy) = __floats2half2_rn(y0, y1);
+        }
+    }
+}
+
+// cluster size for gn_cluster_kernel, or 0 when the shape does not fit it
+static int gn_cluster_size(const GroupNormArgs& a) {
+    static const bool off = getenv("B2_NO_GN_CLUSTER") != nullptr;
+    const int C = a.ca + a.cb;
+    if (off || C % a.groups) return 0;
+    const int cpg = C / a.groups;
+    if ((cpg & 1) || (a.ca & 1) || GNC_THREADS % (cpg >> 1) != 0 || (a.lda & 1) || (a.cb && (a.ldb & 1)) || (a.ldy & 1)) return 0;
+    const long words = (long)a.hw * (cpg >> 1);
+    const long cap = (long)GNC_THREADS * GNC_ITEMS;
+    for (int cl = 1; cl <= 8; cl <<= 1) {
+        const int ppc = (a.hw + cl - 1) / cl;
+        const int pstep = GNC_THREADS / (cpg >> 1);
+        if ((long)((ppc + pstep - 1) / pstep) <= GNC_ITEMS && words <= cap * cl) return cl;
+    }
+    return 0;
+}
+
 size_t groupnorm_partial_floats(int nb, int groups) { return (size_t)nb * GN_MAX_CHUNKS * groups * 2 + 64; }
 
 int groupnorm_launch(const GroupNormArgs& a, cudaStream_t s) {
@@ -348,6 +446,12 @@ int groupnorm_launch(const GroupNormArgs& a, cudaStream_t s) {
         b2_set_error("groupnorm: unsupported channels %d+%d groups %d (need multiples of 8 and a workspace)", a.ca, a.cb,
                      a.groups);
         return -1;
+    }
+    if (const int cl = gn_cluster_size(a)) {
+        const int ppc = (a.hw + cl - 1) / cl;
+        B2_LAUNCHED("gn_cluster", launch_k(gn_cluster_kernel, dim3(a.groups, a.nb, cl), dim3(GNC_THREADS), 0, s, cl, a, ppc));
+        g_gn_last_launches = 1;
+        return 0;
     }
     const int vc = C / 8;
     if (vc > 512) {

@@ -265,10 +265,16 @@ struct b2sd_engine {
     int add_igemm(std::vector<Op>& dst, IgemmDesc d) {
         const bool geglu = (d.epi.flags & IG_GEGLU) != 0;
         const int n_gemm = geglu ? 2 * d.epi.n_valid : d.epi.n_valid;
-        static const bool swap_on = getenv("B2_SWAP") != nullptr;
-        if (swap_on && allow_swap && !geglu && d.epi.n_valid >= 128) {
-            // Swapped orientation (weights on the M side): at batch 1 the UNet has few pixels but many channels, so this is
-            // the way to issue wide (N = 256 pixel) MMAs, read every weight exactly once and still fill the machine.
+        static const bool swap_on = getenv("B2_SWAP") != nullptr, swap_off = getenv("B2_NO_SWAP") != nullptr;
+        static const bool tuned = getenv("B2_NO_TUNED_TILES") == nullptr;
+        int total_kb = 0;
+        for (int sidx = 0; sidx < d.nseg; ++sidx) total_kb += d.ntap[sidx] * (d.src[sidx].C / IG_BK);
+        const long rows_all = (long)d.Nb * d.Ho * d.Wo;
+        // Swapped orientation by default only where it measured faster (tools/bench_op.py, cold weights): the 8x8 level,
+        // where a 128-pixel M tile would be half empty.  B2_SWAP=1 forces it for every eligible UNet contraction.
+        const bool swap_here = allow_swap && !geglu && d.epi.n_valid >= 128 && (d.epi.n_valid & 7) == 0 &&
+                               (swap_on || (!swap_off && tuned && rows_all <= 64 && total_kb >= 90));
+        if (swap_here) {
             IgemmPlan plan;
             const long rows = (long)d.Nb * d.Ho * d.Wo;
             d.swap = 1;
@@ -296,6 +302,33 @@ struct b2sd_engine {
         static const int cands[] = {256, 160, 128, 64, 32, 16};
         int best_bn = 0;
         IgemmPlan plan;
+        if (tuned && !geglu && n_gemm % 160 == 0 && total_kb >= 40) {
+            // K-heavy contractions that cannot fill the GPU with 160-wide tiles alone (batch 1): wide tiles + cluster
+            // split-K beat 64-wide tiles (profiles/r01_tile_sweep.md: -10..-40 % per launch, weights streamed from HBM)
+            d.BN = 160; d.splits = 1; d.partial = nullptr;
+            TRY(igemm_plan(d, &plan));
+            const int m_tiles = plan.p.tiles_w * plan.p.tiles_h * plan.p.tiles_n;
+            const long tiles = (long)m_tiles * (n_gemm / 160);
+            int bn = 0, splits = 0;
+            if (tiles < 132) {
+                if (m_tiles >= 8) { bn = 160; splits = 4; }
+                else if (m_tiles >= 2 && n_gemm % 256 == 0 && total_kb >= 180) { bn = 256; splits = 8; }
+            }
+            if (bn) {
+                d.BN = bn; d.splits = splits;
+                TRY(igemm_plan(d, &plan));
+                best_bn = -1;   // planned
+            }
+        }
+        if (best_bn < 0) {
+            launches += 1;
+            char label[256];
+            snprintf(label, sizeof(label), "igemm %s rows=%ld n=%d kb=%d bn=%d splits=%d grid=%u,%u,%u taps", cur.c_str(),
+                     plan.rows_total, d.epi.n_valid, plan.p.total_kb, plan.p.BN, plan.splits, plan.grid.x, plan.grid.y, plan.grid.z);
+            dst.push_back(Op([plan](cudaStream_t s) { return igemm_launch(plan, s); }, label,
+                             2.0 * (double)plan.rows_total * n_gemm * plan.p.total_kb * IG_BK));
+            return 0;
+        }
         std::vector<int> valid;
         for (int bn : cands) {
             if (geglu && (bn % 32 != 0 || bn < 64)) continue;
@@ -320,6 +353,7 @@ struct b2sd_engine {
             TRY(igemm_plan(d, &plan));
             const long ctas = (long)plan.grid.x * plan.grid.y;
             int splits = ctas >= 96 ? 1 : (int)((148 + ctas - 1) / ctas);
+            if (tuned && ctas >= 64 && total_kb <= 12) splits = 1;   // the cluster reduction (~3 us) costs more than 5 k-blocks
             const int max_by_k = plan.p.total_kb / 4 > 0 ? plan.p.total_kb / 4 : 1;
             if (splits > max_by_k) splits = max_by_k;
             if (splits > 8) splits = 8;

@@ -214,29 +214,111 @@ __device__ __forceinline__ bool epi_fast_ok(const IgEpilogue& e) {
            (e.colbias_bstride & 3) == 0;
 }
 
-// Swapped orientation: the accumulator row is an output CHANNEL, its columns are the pixels of the tile.  16
-// consecutive pixel columns [j0, j0+16) of channel `cout`; consecutive lanes hold consecutive channels, so a warp's
-// 2-byte stores cover 64 contiguous bytes of one pixel row.
-__device__ __forceinline__ void epi_swap16(const IgemmParams& p, const float (&acc)[16], int cout, bool cout_ok, int j0,
-                                           int n0, int h0, int w0) {
+// Swapped orientation: an accumulator row (TMEM lane, thread) is an output CHANNEL, its columns are the pixels of the
+// tile, so the NHWC store needs a transpose.  It goes through a small fp32 shared-memory tile T[pixel][128 channels]:
+// thread r parks its channel's values for a chunk of <= 32 pixels (conflict-free 4-byte stores), then the 128 epilogue
+// threads sweep T row-wise: one thread = 8 consecutive channels of one pixel (16-byte residual load, 16-byte store), a
+// warp = two complete 256-byte pixel rows.  Bias, scale, residual and ReLU are applied in that coalesced sweep.
+constexpr int SWAP_CH = 32;   // pixels per transposition chunk (T = 32 x 128 fp32 = 16 KB)
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// What one thread needs from global memory for its (pixel, 8-channel) items of a chunk: fetched BEFORE the
+// transposition barrier so the latency overlaps the TMEM/DSMEM reads that fill T.
+struct SwapPre {
+    uint4 res[SWAP_CH / 8];
+    float4 b0[SWAP_CH / 8], b1[SWAP_CH / 8];
+    long orow[SWAP_CH / 8];      // < 0: nothing to store
+};
+
+__device__ __forceinline__ void swap_prefetch(const IgemmParams& p, SwapPre& pre, int npix, int j0, int ntile, int n0, int h0,
+                                              int w0, int t) {
     const IgEpilogue& e = p.epi;
     const int tw = 1 << p.tw_log2, th = 1 << p.th_log2;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const int j = j0 + i;
+    for (int k = 0; k < SWAP_CH / 8; ++k) {
+        const int item = t + 128 * k;
+        pre.orow[k] = -1;
+        pre.res[k] = make_uint4(0, 0, 0, 0);
+        pre.b0[k] = pre.b1[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (item >= npix * 16) continue;
+        const int pl = item >> 4, q = item & 15;
+        const int j = j0 + pl;
         const int wi = j & (tw - 1);
         const int hi = (j >> p.tw_log2) & (th - 1);
         const int ni = j >> (p.tw_log2 + p.th_log2);
         const int n = n0 + ni, h = h0 + hi, w = w0 + wi;
-        if (cout_ok && ni < p.tn && n < p.Nb && h < p.Ho && w < p.Wo) {
-            const long orow = ((long)n * p.Ho + h) * p.Wo + w;
-            float v = acc[i];
-            if (e.colbias) v += e.colbias[(long)n * e.colbias_bstride + cout];
-            v *= e.acc_scale;
-            if (e.res) v += e.res_scale * __half2float(e.res[orow * e.ldr + cout]);
-            if (e.flags & IG_RELU) v = fmaxf(v, 0.f);
-            e.out[orow * e.ldc + cout] = __float2half_rn(v);
+        const int cout0 = ntile * IG_BM + q * 8;
+        if (ni >= p.tn || n >= p.Nb || h >= p.Ho || w >= p.Wo || cout0 >= e.n_valid) continue;
+        const long orow = ((long)n * p.Ho + h) * p.Wo + w;
+        pre.orow[k] = orow;
+        if (e.colbias) {
+            const float4* bp = reinterpret_cast<const float4*>(e.colbias + (long)n * e.colbias_bstride + cout0);
+            pre.b0[k] = __ldg(bp);
+            pre.b1[k] = __ldg(bp + 1);
         }
+        if (e.res) pre.res[k] = __ldg(reinterpret_cast<const uint4*>(e.res + orow * e.ldr + cout0));
+    }
+}
+
+__device__ __forceinline__ void swap_store_chunk(const IgemmParams& p, const SwapPre& pre, const float* T, int ntile, int t) {
+    const IgEpilogue& e = p.epi;
+#pragma unroll
+    for (int k = 0; k < SWAP_CH / 8; ++k) {
+        if (pre.orow[k] < 0) continue;
+        const int item = t + 128 * k;
+        const int pl = item >> 4, q = item & 15;
+        const int cout0 = ntile * IG_BM + q * 8;
+        const float4 a0 = *reinterpret_cast<const float4*>(T + pl * IG_BM + q * 8);
+        const float4 a1 = *reinterpret_cast<const float4*>(T + pl * IG_BM + q * 8 + 4);
+        const float4 b0 = pre.b0[k], b1 = pre.b1[k];
+        float v[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w, a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] *= e.acc_scale;
+        if (e.res) {
+            const __half2* rh = reinterpret_cast<const __half2*>(&pre.res[k]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(rh[i]);
+                v[2 * i] += e.res_scale * f.x;
+                v[2 * i + 1] += e.res_scale * f.y;
+            }
+        }
+        if (e.flags & IG_RELU) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        *reinterpret_cast<uint4*>(e.out + pre.orow[k] * e.ldc + cout0) = o;
+    }
+}
+
+// Cluster split-K: sum one 16-column (4 x float4) strip of accumulator row `row` over the K slices held in the peers'
+// shared memory.  All loads of up to four slices are in flight together (a dependent chain of DSMEM round trips was
+// the dominant cost of the reduction); the summation order is fixed => bit-reproducible.
+template <int SPL>
+__device__ __forceinline__ void splitk_sum16(uint32_t stg_local, int cc, int row, float (&acc)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    constexpr int G = SPL < 4 ? SPL : 4;
+#pragma unroll
+    for (int s0 = 0; s0 < SPL; s0 += G) {
+        float4 v[G][4];
+#pragma unroll
+        for (int s = 0; s < G; ++s) {
+            const uint32_t peer = dsmem_map(stg_local, (uint32_t)(s0 + s));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[s][i] = dsmem_ld_f4(peer + (uint32_t)(((cc * 4 + i) * IG_BM + row) * 16));
+        }
+#pragma unroll
+        for (int s = 0; s < G; ++s)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc[4 * i] += v[s][i].x; acc[4 * i + 1] += v[s][i].y; acc[4 * i + 2] += v[s][i].z; acc[4 * i + 3] += v[s][i].w;
+            }
     }
 }
 
@@ -306,6 +388,11 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                 int cb = (kb_begin - base) % p.seg_cblocks[seg];
                 for (int kb = kb_begin; kb < kb_end; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (p.dbg_mode == 1 && kb >= kb_begin + p.num_stages) {   // bound study: operands stay whatever they were
+                        mbar_arrive(&full_bar[stage]);
+                        if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
                     uint8_t* sa = smem + (size_t)stage * stage_bytes;
                     uint8_t* sb = sa + IG_BM * IG_BK * 2;
@@ -356,7 +443,9 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                 const uint64_t da = make_kmajor_sw128_desc(sa);
                 const uint64_t db = make_kmajor_sw128_desc(sa + IG_BM * IG_BK * 2);
                 const uint32_t acc0 = kb > kb_begin ? 1u : 0u;
-                if (elect_one()) {
+                if (p.dbg_mode == 2) {
+                    if (elect_one()) umma_commit(&empty_bar[stage]);
+                } else if (elect_one()) {
                     // +32 B per UMMA_K inside the 128 B swizzle row => +2 in the (addr>>4) field
                     umma_f16(tacc, da, db, idesc, acc0);
                     umma_f16(tacc, da + 2, db + 2, idesc, 1u);
@@ -393,8 +482,6 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
             const long orow = ((long)n * p.Ho + h) * p.Wo + w;
             const uint32_t taddr = tmem_base + (uint32_t)buf * acc_stride + ((uint32_t)(q * 32) << 16);
             if (p.swap) {
-                const int cout = ntile * IG_BM + r;
-                const bool cout_ok = cout < e.n_valid;
                 mbar_wait(&tmem_full_bar[buf], par);
                 tc_fence_after();
                 if (e.flags & IG_SPLITK) {
@@ -409,14 +496,19 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                                                                           __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
                     }
                 } else {
-                    for (int c = 0; c < p.BN; c += 16) {
-                        uint32_t v[16];
-                        tmem_ld16(taddr + c, v);
+                    // the operand ring is idle (every MMA has retired): use its head as the transposition tile
+                    float* T = reinterpret_cast<float*>(smem);
+                    for (int c = 0; c < p.BN; c += SWAP_CH) {
+                        SwapPre pre;
+                        swap_prefetch(p, pre, SWAP_CH, c, ntile, n0, h0, w0, r);
+                        uint32_t v[32];
+                        tmem_ld32(taddr + c, v);
                         tmem_ld_wait();
-                        float acc[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(v[i]);
-                        epi_swap16(p, acc, cout, cout_ok, c, n0, h0, w0);
+                        for (int i = 0; i < 32; ++i) T[i * IG_BM + r] = __uint_as_float(v[i]);
+                        epi_bar_sync();
+                        swap_store_chunk(p, pre, T, ntile, r);
+                        epi_bar_sync();
                     }
                 }
             } else if (epi_fast_ok(e)) {
@@ -485,7 +577,52 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
         const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
         const int splits = (int)gridDim.z;
         cluster_sync_all();  // all partial tiles are in place (release/acquire over the cluster)
-        if (warp >= 2) {
+        B2_TS(if (ts && threadIdx.x == 64) ts[6] = globaltimer_ns();)   // split launches: [5] staged, [6] cluster barrier passed, [7] reduced
+        if (warp >= 2 && p.swap) {
+            // swapped orientation: this CTA finalises the pixel columns [rank*cols_per, (rank+1)*cols_per) of the tile
+            const int rank = (int)cluster_ctarank();
+            const int cols_per = p.BN / splits;
+            const int ch = cols_per < SWAP_CH ? cols_per : SWAP_CH;
+            const int t = threadIdx.x - 64;               // 0..127 == accumulator row == output channel of the tile
+            const uint32_t stg_local = smem_u32(smem);
+            float* T = reinterpret_cast<float*>(smem + (size_t)p.BN * IG_BM * 4);   // right after the staging tile
+            for (int c = rank * cols_per; c < (rank + 1) * cols_per; c += ch) {
+                SwapPre pre;
+                swap_prefetch(p, pre, ch, c, ntile, n0, h0, w0, t);
+                for (int g = 0; g < (ch >> 2); g += 4) {     // 16 pixel columns per pass (ch is 8, 16 or 32)
+                    float acc[16];
+                    const int cc = ((c >> 2) + g) >> 2;      // 16-column strip index (c is a multiple of 16 when ch >= 16)
+                    if (ch >= 16) {
+                        switch (splits) {
+                            case 2: splitk_sum16<2>(stg_local, cc, t, acc); break;
+                            case 4: splitk_sum16<4>(stg_local, cc, t, acc); break;
+                            default: splitk_sum16<8>(stg_local, cc, t, acc); break;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) T[(4 * g + i) * IG_BM + t] = acc[i];
+                    } else {
+                        // 8 pixel columns per CTA (BN 64 over 8 slices): two float4 groups
+#pragma unroll
+                        for (int gg = 0; gg < 2; ++gg) {
+                            float4 v[8];
+#pragma unroll
+                            for (int sidx = 0; sidx < 8; ++sidx)
+                                v[sidx] = dsmem_ld_f4(dsmem_map(stg_local, (uint32_t)sidx) + (uint32_t)((((c >> 2) + gg) * IG_BM + t) * 16));
+                            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int sidx = 0; sidx < 8; ++sidx) { a.x += v[sidx].x; a.y += v[sidx].y; a.z += v[sidx].z; a.w += v[sidx].w; }
+                            T[(4 * gg + 0) * IG_BM + t] = a.x;
+                            T[(4 * gg + 1) * IG_BM + t] = a.y;
+                            T[(4 * gg + 2) * IG_BM + t] = a.z;
+                            T[(4 * gg + 3) * IG_BM + t] = a.w;
+                        }
+                    }
+                }
+                epi_bar_sync();
+                swap_store_chunk(p, pre, T, ntile, t);
+                epi_bar_sync();
+            }
+        } else if (warp >= 2) {
             const int rank = (int)cluster_ctarank();
             const int rows_per = IG_BM / splits;          // splits in {2,4,8}
             const int t = threadIdx.x - 64;               // 0..127
@@ -499,26 +636,21 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                 const int n = n0 + ni, h = h0 + hi, w = w0 + wi;
                 const bool ok = (ni < p.tn) && (n < p.Nb) && (h < p.Ho) && (w < p.Wo);
                 float acc[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-                for (int sidx = 0; sidx < splits; ++sidx) {   // fixed order => bit-reproducible
-                    const uint32_t peer = dsmem_map(stg_local, (uint32_t)sidx);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 v = dsmem_ld_f4(peer + (uint32_t)(((cc * 4 + i) * IG_BM + r) * 16));
-                        acc[4 * i] += v.x; acc[4 * i + 1] += v.y; acc[4 * i + 2] += v.z; acc[4 * i + 3] += v.w;
-                    }
+                switch (splits) {
+                    case 2: splitk_sum16<2>(stg_local, cc, r, acc); break;
+                    case 4: splitk_sum16<4>(stg_local, cc, r, acc); break;
+                    default: splitk_sum16<8>(stg_local, cc, r, acc); break;
                 }
-                if (p.swap) epi_swap16(p, acc, ntile * IG_BM + r, ntile * IG_BM + r < p.epi.n_valid, cc * 16, n0, h0, w0);
-                else if (ok) epi_store16<0>(p.epi, acc, n, ((long)n * p.Ho + h) * p.Wo + w, ntile * p.BN + cc * 16);
+                if (ok) epi_store16<0>(p.epi, acc, n, ((long)n * p.Ho + h) * p.Wo + w, ntile * p.BN + cc * 16);
             }
         }
+        B2_TS(if (ts && threadIdx.x == 64) ts[7] = globaltimer_ns();)
         cluster_sync_all();  // nobody may exit while a peer still reads its shared memory
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
-    B2_TS(if (ts && threadIdx.x == 32) ts[7] = globaltimer_ns();)
+    B2_TS(if (ts && threadIdx.x == 32 && !(p.epi.flags & IG_SPLITK)) ts[7] = globaltimer_ns();)
 }
 
 // ------------------------------------------------------------------------------------------
@@ -936,6 +1068,7 @@ static int plan_swap(const IgemmDesc& d, IgemmPlan* plan) {
         return -1;
     }
     p.swap = 1;
+    { static const char* dm = getenv("B2_DBG_MODE"); p.dbg_mode = dm ? atoi(dm) : 0; }
     p.kpack = 1;
     p.acc_bufs = 1;
     p.BN = BN;
@@ -988,16 +1121,26 @@ static int plan_swap(const IgemmDesc& d, IgemmPlan* plan) {
     if (splits > 1) p.epi.flags |= IG_SPLITK;
     const int c_tiles = (d.epi.n_valid + IG_BM - 1) / IG_BM;
     p.n_pad = c_tiles * IG_BM;
+    if ((d.epi.n_valid & 7) || (d.epi.ldc & 7) || (d.epi.res && (d.epi.ldr & 7)) || (d.epi.colbias && (d.epi.colbias_bstride & 3)) ||
+        (reinterpret_cast<uintptr_t>(d.epi.out) & 15) || (reinterpret_cast<uintptr_t>(d.epi.res) & 15) ||
+        (reinterpret_cast<uintptr_t>(d.epi.colbias) & 15)) {
+        b2_set_error("igemm(swap): epilogue needs n_valid/ldc/ldr multiples of 8 and 16-byte aligned pointers");
+        return -1;
+    }
     const size_t stage_bytes = (size_t)IG_BM * IG_BK * 2 + (size_t)BN * IG_BK * 2;
-    int stages = (int)((100 * 1024) / stage_bytes);
+    // swapped launches are small grids (<= ~1 CTA per SM): give the ring most of the shared memory
+    static const char* sw_stage_env = getenv("B2_SWAP_STAGE_KB");
+    int stages = (int)(((size_t)(sw_stage_env ? atoi(sw_stage_env) : 200) * 1024) / stage_bytes);
     if (stages < 2) stages = 2;
     if (stages > IG_MAX_STAGES) stages = IG_MAX_STAGES;
     if (stages > p.kb_per_split) stages = p.kb_per_split < 2 ? 2 : p.kb_per_split;
     size_t pipe_bytes = stages * stage_bytes;
-    if (splits > 1) {
-        const size_t stg = (size_t)BN * IG_BM * 4;
-        if (stg > pipe_bytes) {
-            stages = (int)((stg + stage_bytes - 1) / stage_bytes);
+    {
+        // epilogue scratch carved out of the ring: [split-K staging tile BN x 128 fp32] + transposition tile (<= 32 x 128 fp32)
+        const int cols_per = BN / splits;
+        const size_t need = (splits > 1 ? (size_t)BN * IG_BM * 4 : 0) + (size_t)(cols_per < SWAP_CH ? cols_per : SWAP_CH) * IG_BM * 4;
+        if (need > pipe_bytes) {
+            stages = (int)((need + stage_bytes - 1) / stage_bytes);
             if (stages > IG_MAX_STAGES) {
                 b2_set_error("igemm(swap): split-K staging does not fit (BN %d)", BN);
                 return -1;
@@ -1040,6 +1183,7 @@ int igemm_plan(const IgemmDesc& d, IgemmPlan* plan) {
         return -1;
     }
     p.BN = BN;
+    { static const char* dm = getenv("B2_DBG_MODE"); p.dbg_mode = dm ? atoi(dm) : 0; }
     const int n_tiles = (n_gemm + BN - 1) / BN;
     if (d.w_rows < n_gemm) {
         // TMA zero-fills rows beyond w_rows; allowed (padded N) but flag obviously wrong descs
@@ -1138,7 +1282,8 @@ int igemm_plan(const IgemmDesc& d, IgemmPlan* plan) {
     // most ~1 CTA per SM take the whole shared memory for the ring; with many CTAs keep two co-resident instead.
     const long total_ctas = (long)p.tiles_w * p.tiles_h * p.tiles_n * n_tiles * splits;
     static const char* stage_env = getenv("B2_STAGE_KB");
-    const size_t ring_budget = stage_env ? (size_t)atoi(stage_env) * 1024 : (size_t)(100 * 1024);
+    // <= 1 CTA per SM anyway: take (nearly) all the shared memory for the ring, the mainloop is TMA-latency bound
+    const size_t ring_budget = stage_env ? (size_t)atoi(stage_env) * 1024 : (size_t)((total_ctas <= 148 ? 200 : 100) * 1024);
     int stages = (int)(ring_budget / stage_bytes);
     if (stages < 2) stages = 2;
     if (stages > IG_MAX_STAGES) stages = IG_MAX_STAGES;

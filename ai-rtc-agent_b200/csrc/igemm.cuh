@@ -65,6 +65,7 @@ struct IgemmParams {
     int n_pad;
     int swap;                     // 1: weights on the M side (128 output channels per CTA), pixels on the N side
     int tw_log2, th_log2;         // swap mode: pixel-tile extents are powers of two
+    int dbg_mode;                 // bound study (env B2_DBG_MODE): 1 = TMA loads only for the first ring pass, 2 = no MMAs
     IgEpilogue epi;
 };
 

@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libb200sd.so")
+# B200SD_LIB: developer override (e.g. the -DB2_TIMELINE build used by tools/timeline_chain.py)
+LIB_PATH = os.environ.get("B200SD_LIB") or os.path.join(os.path.dirname(_HERE), "libb200sd.so")
 
 
 class B2Error(RuntimeError):

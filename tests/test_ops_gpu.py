@@ -82,6 +82,8 @@ def test_cross_attention_shared_kv(cuda, nb, heads, seq, d, dp, skv):
     (1, 64, 64, 320, 0, True, 1e-5), (2, 32, 32, 640, 0, False, 1e-6), (1, 16, 16, 1280, 1280, True, 1e-5),
     (1, 32, 32, 1280, 640, True, 1e-5),   # 1920 channels: groups of 60 straddle the concat boundary
     (4, 8, 8, 1280, 0, True, 1e-5), (1, 24, 24, 640, 320, True, 1e-5),
+    (1, 64, 64, 640, 320, True, 1e-5),    # cluster of 8 CTAs per group
+    (1, 8, 8, 1280, 1280, True, 1e-5), (1, 96, 96, 640, 320, True, 1e-5),   # too large for a cluster: whole-grid kernel
 ])
 def test_groupnorm(cuda, nb, h, w, ca, cb, silu, eps):
     ops = _ops()

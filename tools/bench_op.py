@@ -14,6 +14,21 @@ def timeit(fn, iters=50):
     for _ in range(iters): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters * 1000
+def timeit_graph(fn, n):
+    """n calls captured into one CUDA graph (no host planning/launch cost in the timed region)"""
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    st = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(st):
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(n): fn()
+    g.replay(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3): g.replay()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (3 * n) * 1000
 def conv_case(nb, h, w, cin, cout, bn, splits, res=False, relu=False):
     x = rnd(nb, h, w, cin); wt = ops.pack_conv_weight(rnd(cout, cin, 3, 3, scale=(9*cin) ** -0.5)); b = torch.randn(1, cout, device=dev)
     y = torch.empty(nb, h, w, cout, device=dev, dtype=torch.float16)
@@ -22,6 +37,68 @@ def conv_case(nb, h, w, cin, cout, bn, splits, res=False, relu=False):
     us = timeit(lambda: ops.igemm([(x, 9)], wt, y, colbias=b, bn=bn, splits=splits, res=x if res else None, relu=relu))
     fl = 2.0 * nb * h * w * cout * cin * 9
     print(f"conv {nb}x{h}x{w} {cin}->{cout} bn={bn} splits={splits}: {us:8.1f} us  {fl/us/1e6:7.1f} TF/s")
+
+def conv_cold(nb, h, w, cin, cout, bn, splits, swap, taps=9, res=True):
+    """weights rotate over > 2x L2 so every launch streams them from HBM like the real frame does"""
+    wbytes = cout * cin * taps * 2
+    ncopy = max(2, min(64, int(300e6 // wbytes) + 1))
+    x = rnd(nb, h, w, cin)
+    if taps == 9: wts = [ops.pack_conv_weight(rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5)) for _ in range(ncopy)]
+    else: wts = [rnd(cout, cin, scale=cin ** -0.5) for _ in range(ncopy)]
+    b = torch.randn(1, cout, device=dev); r = rnd(nb, h, w, cout) if res else None
+    y = torch.empty(nb, h, w, cout, device=dev, dtype=torch.float16)
+    it = [0]
+    def fn():
+        it[0] += 1
+        ops.igemm([(x, taps)], wts[it[0] % ncopy], y, colbias=b, bn=bn, splits=splits, res=r, swap=swap)
+    us = timeit_graph(fn, 2 * ncopy)
+    fl = 2.0 * nb * h * w * cout * cin * taps
+    print(f"{'swap' if swap else 'base'} taps={taps} {nb}x{h}x{w} {cin}->{cout} bn={bn} splits={splits}: {us:8.1f} us  {fl/us/1e6:7.1f} TF/s  {wbytes/us/1e3:7.1f} GB/s(w)", flush=True)
+if "gn" in sys.argv:
+    for args in [(1, 64, 64, 320), (1, 64, 64, 640, 320), (1, 64, 64, 320, 320), (1, 32, 32, 640), (1, 32, 32, 1280, 640), (1, 16, 16, 1280), (1, 16, 16, 1280, 1280), (1, 8, 8, 1280, 1280), (4, 64, 64, 320)]:
+        xa = rnd(*args[:4]); cb = args[4] if len(args) > 4 else 0; xb = rnd(args[0], args[1], args[2], cb) if cb else None
+        c = args[3] + cb; g = torch.ones(c, device=dev); b = torch.zeros(c, device=dev); y = torch.empty(args[0], args[1], args[2], c, device=dev, dtype=torch.float16)
+        print(f"groupnorm {args}: {timeit_graph(lambda: ops.groupnorm(xa, xb, g, b, y), 20):7.2f} us per launch (chain of 20 in a graph)", flush=True)
+    sys.exit(0)
+if "tilesweep" in sys.argv:
+    print("B2_STAGE_KB =", os.environ.get("B2_STAGE_KB", "default"))
+    for (h, cin, cout, taps) in [(64, 320, 320, 9), (64, 640, 320, 9), (64, 960, 320, 9), (64, 320, 320, 1), (64, 1280, 320, 1),
+                                 (32, 640, 640, 9), (32, 1280, 640, 9), (32, 640, 640, 1), (32, 2560, 640, 1),
+                                 (16, 1280, 1280, 9), (16, 2560, 1280, 9), (16, 1280, 1280, 1), (16, 5120, 1280, 1), (8, 1280, 1280, 9)]:
+        mt = (h * h + 127) // 128
+        for bn in [64, 128, 160, 256]:
+            if cout % bn: continue
+            for sp in [1, 2, 4, 8]:
+                ctas = mt * (cout // bn) * sp
+                if ctas > 320 or ctas < 48 or sp * 4 > cin * taps // 64: continue
+                try: conv_cold(1, h, h, cin, cout, bn, sp, False, taps)
+                except Exception as e: print("fail", h, cin, cout, bn, sp, str(e)[:80])
+    sys.exit(0)
+if "boundstudy" in sys.argv:
+    print("B2_DBG_MODE =", os.environ.get("B2_DBG_MODE", "0"), "(0 normal, 1 no TMA after first ring pass, 2 no MMAs)")
+    for (h, cin, cout, taps, bn, sp, sw) in [(64, 320, 320, 9, 64, 1, False), (64, 320, 320, 9, 160, 1, False), (64, 320, 320, 9, 128, 1, True), (64, 320, 320, 9, 256, 2, True),
+                                             (32, 640, 640, 9, 64, 2, False), (32, 640, 640, 9, 256, 4, True),
+                                             (16, 1280, 1280, 9, 64, 4, False), (16, 1280, 1280, 9, 256, 8, True), (16, 1280, 1280, 9, 128, 4, True),
+                                             (8, 1280, 1280, 9, 64, 8, False), (8, 1280, 1280, 9, 64, 8, True),
+                                             (64, 320, 320, 1, 64, 1, False), (16, 1280, 1280, 1, 64, 4, False), (16, 1280, 1280, 1, 128, 4, True)]:
+        conv_cold(1, h, h, cin, cout, bn, sp, sw, taps)
+    sys.exit(0)
+if "swapsweep" in sys.argv:
+    for (h, cin, cout, taps) in [(64, 320, 320, 9), (64, 320, 320, 1), (64, 1280, 320, 1), (32, 640, 640, 9), (32, 640, 640, 1), (32, 2560, 640, 1),
+                                 (16, 1280, 1280, 9), (16, 1280, 1280, 1), (16, 5120, 1280, 1), (8, 1280, 1280, 9), (8, 2560, 1280, 9)]:
+        rows = h * h
+        base = {64: [(64, 1)], 32: [(64, 2), (128, 2)], 16: [(64, 4), (128, 8)], 8: [(64, 8)]}[h]
+        for bn, sp in base:
+            try: conv_cold(1, h, h, cin, cout, bn, sp, False, taps)
+            except Exception as e: print("fail base", h, cin, cout, bn, sp, str(e)[:80])
+        sbn = 256 if rows >= 256 else 64
+        for bn in ([256, 128] if rows >= 256 else [64]):
+            for sp in [1, 2, 4, 8]:
+                ctas = ((rows + bn - 1) // bn) * ((cout + 127) // 128) * sp
+                if ctas > 320 or (ctas < 40 and sp < 8): continue
+                try: conv_cold(1, h, h, cin, cout, bn, sp, True, taps)
+                except Exception as e: print("fail swap", h, cin, cout, bn, sp, str(e)[:80])
+    sys.exit(0)
 import itertools
 if "sweep" in sys.argv:
     for (h, c) in [(64, 320), (32, 640), (16, 1280), (8, 1280)]:
@@ -38,7 +115,7 @@ for args in [(1,512,512,64,64,64,1,True,True), (1,256,256,64,64,64,1,True,True),
 def gn_case(nb, h, w, c, cb=0):
     xa = rnd(nb, h, w, c); xb = rnd(nb, h, w, cb) if cb else None
     g = torch.ones(c + cb, device=dev); b = torch.zeros(c + cb, device=dev); y = torch.empty(nb, h, w, c + cb, device=dev, dtype=torch.float16)
-    us = timeit(lambda: ops.groupnorm(xa, xb, g, b, y))
+    us = timeit_graph(lambda: ops.groupnorm(xa, xb, g, b, y), 20)
     print(f"groupnorm {nb}x{h}x{w}x{c}+{cb}: {us:7.1f} us  ({(xa.numel() + (xb.numel() if cb else 0)) * 4 / us / 1e3:6.1f} GB/s r+w)")
 def ln_case(rows, c):
     x = rnd(rows, c); g = torch.ones(c, device=dev); b = torch.zeros(c, device=dev); y = torch.empty_like(x)
