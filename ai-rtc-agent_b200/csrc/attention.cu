@@ -13,9 +13,15 @@ namespace b2 {
 
 constexpr int AT_BQ = 128;      // query rows per CTA == UMMA M
 constexpr int AT_STAGES = 2;    // K/V ring depth
-constexpr int AT_THREADS = 192; // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2-5 softmax
+constexpr int AT_THREADS = 320; // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2-9 softmax (two warps per TMEM lane quarter)
+constexpr int AT_SM_THREADS = 256;
 // TMEM: S (one QK^T tile, BKV columns) at column 0, O accumulator (DP columns) right after it; 256 columns per
 // CTA so that two CTAs share an SM (one's softmax overlaps the other's MMAs).
+// Softmax: a query row (TMEM lane) is shared by TWO threads (warps w and w+4 see the same lane quarter), each owning half
+// of the S columns / O columns.  One warp per scheduler was pure latency (tcgen05.ld -> max chain -> ex2 chain): measured
+// on B200, 288 CTAs (two per SM) took exactly as long as 128 (one per SM), so the second warp per scheduler is free.
+// The pair only exchanges its block maximum (fp16, 512 B of shared memory, one 64-thread named barrier per KV block);
+// the row sums stay private until the end.
 constexpr uint32_t AT_TMEM_COLS = 256;
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -23,6 +29,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+
+template <bool V> struct AttnTag { static constexpr bool value = V; };
 
 struct AttnParams {
     CUtensorMap tmq, tmk, tmv;
@@ -34,7 +42,7 @@ struct AttnParams {
 };
 
 template <int DA, int BKV>
-__global__ void __launch_bounds__(AT_THREADS) attn_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(AT_THREADS, (DA == 1 ? 2 : 1)) attn_kernel(const __grid_constant__ AttnParams p) {
     constexpr int DP = DA * 64;
     constexpr int KVA = BKV / 64;                       // kv atoms per block (P / V^T tiles)
     constexpr uint32_t Q_BYTES = DA * AT_BQ * 128;      // DA atoms of [128 rows][128 B]
@@ -49,13 +57,16 @@ __global__ void __launch_bounds__(AT_THREADS) attn_kernel(const __grid_constant_
     uint8_t* sP = sKV + AT_STAGES * STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
     uint64_t* q_full = bars;
-    uint64_t* kv_full = bars + 1;               // [AT_STAGES]
-    uint64_t* kv_empty = kv_full + AT_STAGES;   // [AT_STAGES]
-    uint64_t* s_full = kv_empty + AT_STAGES;
+    uint64_t* k_full = bars + 1;                // [AT_STAGES]  K and V^T tiles travel through separate rings: a K slot is
+    uint64_t* k_empty = k_full + AT_STAGES;     // [AT_STAGES]  free as soon as QK^T(j) retires, one softmax earlier than the
+    uint64_t* v_full = k_empty + AT_STAGES;     // [AT_STAGES]  V slot, so K(j+2) is requested ~1.3 KV blocks before its use
+    uint64_t* v_empty = v_full + AT_STAGES;     // [AT_STAGES]  (with one shared ring the K latency was exposed every block)
+    uint64_t* s_full = v_empty + AT_STAGES;
     uint64_t* s_empty = s_full + 1;
     uint64_t* p_full = s_empty + 1;
     uint64_t* o_done = p_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+    float* xch = reinterpret_cast<float*>(bars + 32);          // 512 B pair-exchange scratch: [2][128] fp16 maxima / [128] fp32 sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * AT_BQ;
@@ -72,12 +83,14 @@ __global__ void __launch_bounds__(AT_THREADS) attn_kernel(const __grid_constant_
         tma_prefetch_desc(&p.tmv);
         mbar_init(q_full, 1);
         for (int s = 0; s < AT_STAGES; ++s) {
-            mbar_init(&kv_full[s], 1);
-            mbar_init(&kv_empty[s], 1);
+            mbar_init(&k_full[s], 1);
+            mbar_init(&k_empty[s], 1);
+            mbar_init(&v_full[s], 1);
+            mbar_init(&v_empty[s], 1);
         }
         mbar_init(s_full, 1);
-        mbar_init(s_empty, 128);
-        mbar_init(p_full, 128);
+        mbar_init(s_empty, AT_SM_THREADS);
+        mbar_init(p_full, AT_SM_THREADS);
         mbar_init(o_done, 1);
         fence_mbar_init();
     }
@@ -99,20 +112,29 @@ __global__ void __launch_bounds__(AT_THREADS) attn_kernel(const __grid_constant_
 #pragma unroll
             for (int a = 0; a < DA; ++a)
                 tma_load_2d(sQ + a * (AT_BQ * 128), &p.tmq, q_full, h * DP + a * 64, b * p.sq + q0);
-            for (int j = 0; j < nblk; ++j) {
+            auto load_k = [&](int j) {
                 const int st = j % AT_STAGES;
-                mbar_wait(&kv_empty[st], ((j / AT_STAGES) & 1) ^ 1);
+                mbar_wait(&k_empty[st], ((j / AT_STAGES) & 1) ^ 1);
                 uint8_t* sk = sKV + st * STAGE_BYTES;
-                uint8_t* sv = sk + K_BYTES;
-                mbar_expect_tx(&kv_full[st], STAGE_BYTES);
+                mbar_expect_tx(&k_full[st], K_BYTES);
 #pragma unroll
                 for (int a = 0; a < DA; ++a)
-                    tma_load_2d(sk + a * (BKV * 128), &p.tmk, &kv_full[st], h * DP + a * 64,
-                                (int)(b * p.k_bstride) + j * BKV);
+                    tma_load_2d(sk + a * (BKV * 128), &p.tmk, &k_full[st], h * DP + a * 64, (int)(b * p.k_bstride) + j * BKV);
+            };
+            auto load_v = [&](int j) {
+                const int st = j % AT_STAGES;
+                mbar_wait(&v_empty[st], ((j / AT_STAGES) & 1) ^ 1);
+                uint8_t* sv = sKV + st * STAGE_BYTES + K_BYTES;
+                mbar_expect_tx(&v_full[st], V_BYTES);
 #pragma unroll
                 for (int a = 0; a < KVA; ++a)
-                    tma_load_2d(sv + a * (DP * 128), &p.tmv, &kv_full[st],
-                                (int)(b * p.vt_bstride) + j * BKV + a * 64, h * DP);
+                    tma_load_2d(sv + a * (DP * 128), &p.tmv, &v_full[st], (int)(b * p.vt_bstride) + j * BKV + a * 64, h * DP);
+            };
+            // issue order = the order in which slots become free: K(j+1) [after QK(j-1)] before V(j) [after PV(j-2)]
+            load_k(0);
+            for (int j = 0; j < nblk; ++j) {
+                if (j + 1 < nblk) load_k(j + 1);
+                load_v(j);
             }
         }
     } else if (warp == 1) {
@@ -123,7 +145,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_kernel(const __grid_constant_
         const uint32_t sq_addr = smem_u32(sQ), skv_addr = smem_u32(sKV), sp_addr = smem_u32(sP);
         auto issue_qk = [&](int j) {
             const int st = j % AT_STAGES;
-            mbar_wait(&kv_full[st], (j / AT_STAGES) & 1);
+            mbar_wait(&k_full[st], (j / AT_STAGES) & 1);
             mbar_wait(s_empty, (j & 1) ^ 1);
             tc_fence_after();
             const uint32_t sk = skv_addr + st * STAGE_BYTES;
@@ -136,6 +158,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_kernel(const __grid_constant_
                     for (int k = 0; k < 4; ++k) umma_f16(tmem_base, dq + 2 * k, dk + 2 * k, idesc_s, (a | k) ? 1u : 0u);
                 }
                 umma_commit(s_full);
+                umma_commit(&k_empty[st]);
             }
             __syncwarp();
         };
@@ -144,6 +167,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_kernel(const __grid_constant_
         for (int j = 0; j < nblk; ++j) {
             if (j + 1 < nblk) issue_qk(j + 1);  // issues as soon as softmax(j) has drained S; overlaps its P stores
             const int st = j % AT_STAGES;
+            mbar_wait(&v_full[st], (j / AT_STAGES) & 1);
             mbar_wait(p_full, j & 1);
             tc_fence_after();
             const uint32_t sv = skv_addr + st * STAGE_BYTES + K_BYTES;
@@ -157,111 +181,129 @@ __global__ void __launch_bounds__(AT_THREADS) attn_kernel(const __grid_constant_
                         umma_f16(tmem_base + BKV, dp + 2 * k, dv + 2 * k, idesc_o, (j > 0 || a > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(o_done);
-                umma_commit(&kv_empty[st]);
+                umma_commit(&v_empty[st]);
             }
             __syncwarp();
         }
     } else {
-        // ===== softmax / correction / epilogue: thread owns query row r =====
-        const int q = warp & 3;
+        // ===== softmax / correction / epilogue: threads (hf = 0, 1) of a pair own query row r, columns [hf*HC, hf*HC + HC) =====
+        constexpr int HC = BKV / 2;           // S columns per thread
+        constexpr int HO = DP / 2;            // O columns per thread
+        const int q = warp & 3;               // TMEM lane quarter this warp may access
+        const int hf = (warp - 2) >> 2;
         const int r = q * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         float m_run = -INFINITY, l_run = 0.f;
-        const uint32_t tS = lane_addr;
-        const uint32_t tO = lane_addr + BKV;
-        for (int j = 0; j < nblk; ++j) {
+        const uint32_t tS = lane_addr + hf * HC;
+        const uint32_t tO = lane_addr + BKV + hf * HO;
+        __half* xmax = reinterpret_cast<__half*>(xch);
+        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };
+        // one KV block; MASKED is a compile-time flag so that interior blocks carry no per-element compare/select at all
+        auto block = [&](int j, auto masked_tag) {
+            constexpr bool MASKED = decltype(masked_tag)::value;
             const int kv_valid = p.skv - j * BKV;  // columns >= kv_valid are masked
-            const bool full = kv_valid >= BKV;     // warp-uniform: interior blocks skip all masking
             mbar_wait(s_full, j & 1);
             tc_fence_after();
-            // pass 1: row max
-            float mx = -INFINITY;
+            // pass 1: maximum of this thread's columns (kept in registers for pass 2), four independent chains
+            uint32_t v[HC];
 #pragma unroll
-            for (int c = 0; c < BKV; c += 32) {
-                uint32_t v[32];
-                tmem_ld32(tS + c, v);
-                tmem_ld_wait();
-                if (full) {
+            for (int c = 0; c < HC; c += 32) tmem_ld32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&v[c]));
+            tmem_ld_wait();
+            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-                }
+            for (int i = 0; i < HC; ++i) {
+                if (!MASKED || hf * HC + i < kv_valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
             }
-            const float m_new = fmaxf(m_run, mx * p.scale_log2);
+            // S(j) is in registers: the next QK^T may overwrite it
+            tc_fence_before();
+            mbar_arrive(s_empty);
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            // pair exchange in fp16, rounded UP so that exp2 arguments stay <= 0 (any common m is a valid softmax shift).
+            // Single buffer is race free: the partner reads before it arrives on s_empty(j), and this thread's next write
+            // happens after s_full(j+1), which needs every s_empty(j) arrival.
+            const __half mh = __float2half_ru(fmaxf(mx, -60000.f));
+            xmax[hf * AT_BQ + r] = mh;
+            pair_sync();
+            const float mpair = fmaxf(__half2float(mh), __half2float(xmax[(hf ^ 1) * AT_BQ + r]));
+            const float m_new = fmaxf(m_run, mpair * p.scale_log2);
             const float alpha = ex2_approx(m_run - m_new);
             if (j > 0) mbar_wait(o_done, (j - 1) & 1);  // PV(j-1) retired: P buffer + O are ours
             // pass 2: P = exp2(s*scale - m), to smem (fp16, swizzled K-major), row sum
-            float rs = 0.f;
+            float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int c = 0; c < BKV; c += 32) {
-                uint32_t v[32];
-                tmem_ld32(tS + c, v);
-                tmem_ld_wait();
+            for (int c = 0; c < HC; c += 32) {
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                    float p0 = ex2_approx(__uint_as_float(v[i]) * p.scale_log2 - m_new);
-                    float p1 = ex2_approx(__uint_as_float(v[i + 1]) * p.scale_log2 - m_new);
-                    if (!full) {
-                        if (c + i >= kv_valid) p0 = 0.f;
-                        if (c + i + 1 >= kv_valid) p1 = 0.f;
+                    float p0 = ex2_approx(__uint_as_float(v[c + i]) * p.scale_log2 - m_new);
+                    float p1 = ex2_approx(__uint_as_float(v[c + i + 1]) * p.scale_log2 - m_new);
+                    if (MASKED) {
+                        if (hf * HC + c + i >= kv_valid) p0 = 0.f;
+                        if (hf * HC + c + i + 1 >= kv_valid) p1 = 0.f;
                     }
-                    rs += p0 + p1;
+                    rs4[(i >> 1) & 3] += p0 + p1;
                     const __half2 hp = __floats2half2_rn(p0, p1);
                     pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
                 }
-                const int atom = c >> 6;
-                uint8_t* prow = sP + atom * (AT_BQ * 128);
+                const int cabs = hf * HC + c;      // column inside the KV block
+                uint8_t* prow = sP + (cabs >> 6) * (AT_BQ * 128);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const uint32_t chunk = ((c & 63) >> 3) + u;
+                    const uint32_t chunk = ((cabs & 63) >> 3) + u;
                     *reinterpret_cast<uint4*>(prow + sw128_offset(r, chunk)) =
                         make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
                 }
             }
-            // S(j) fully consumed: the next QK^T may overwrite it
-            tc_fence_before();
-            mbar_arrive(s_empty);
-            // rescale the running O accumulator (TMEM) when any row of this warp moved its max
+            // rescale this thread's half of the running O accumulator (TMEM) when any row of the warp moved its max
             if (j > 0) {
                 const bool need = __any_sync(0xffffffffu, alpha != 1.0f);
                 if (need) {
 #pragma unroll
-                    for (int c = 0; c < DP; c += 32) {
-                        uint32_t v[32];
-                        tmem_ld32(tO + c, v);
+                    for (int c = 0; c < HO; c += 32) {
+                        uint32_t o[32];
+                        tmem_ld32(tO + c, o);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-                        tmem_st32(tO + c, v);
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st32(tO + c, o);
                     }
                     tmem_st_wait();
                 }
             }
-            l_run = l_run * alpha + rs;
+            l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
             m_run = m_new;
             fence_proxy_async_smem();  // P stores -> visible to the UMMA (async proxy)
             tc_fence_before();
             mbar_arrive(p_full);
+        };
+        for (int j = 0; j < nblk; ++j) {
+            if (p.skv - j * BKV >= BKV) block(j, AttnTag<false>{});   // warp-uniform
+            else block(j, AttnTag<true>{});
         }
-        // epilogue: O / l -> fp16 -> global
+        // row sum of the pair (both halves used the same running maximum, so the partial sums simply add)
+        pair_sync();                       // nobody still reads the fp16 maxima
+        if (hf == 1) xch[r] = l_run;
+        pair_sync();
+        if (hf == 0) { l_run += xch[r]; }
+        pair_sync();
+        if (hf == 0) xch[r] = l_run;
+        pair_sync();
+        l_run = xch[r];
+        // epilogue: O / l -> fp16 -> global (this thread's half of the head dimension)
         mbar_wait(o_done, (nblk - 1) & 1);
         tc_fence_after();
         const float inv_l = 1.0f / l_run;
         const bool row_ok = (q0 + r) < p.sq;
         __half* orow = p.out + ((long)b * p.sq + q0 + r) * p.ldo + h * p.d_real;
 #pragma unroll
-        for (int c = 0; c < DP; c += 32) {
+        for (int c = 0; c < HO; c += 32) {
             uint32_t v[32];
-            tmem_ld32(lane_addr + BKV + c, v);
+            tmem_ld32(tO + c, v);
             tmem_ld_wait();
             if (row_ok) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int col = c + 8 * u;
+                    const int col = hf * HO + c + 8 * u;
                     if (col + 8 <= p.d_real) {
                         uint4 o;
                         __half2* oh = reinterpret_cast<__half2*>(&o);
@@ -314,7 +356,7 @@ static size_t attn_smem_bytes(int da, int bkv) {
     const size_t k = (size_t)da * bkv * 128;
     const size_t v = (size_t)(bkv / 64) * da * 64 * 128;
     const size_t pb = (size_t)(bkv / 64) * AT_BQ * 128;
-    return q + AT_STAGES * (k + v) + pb + 256;
+    return q + AT_STAGES * (k + v) + pb + 256 + 512;   // + barriers + pair-exchange scratch (2 CTAs of <1,128> still fit an SM)
 }
 
 int attn_plan(const AttnDesc& d, AttnPlan* plan) {

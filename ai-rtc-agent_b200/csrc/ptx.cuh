@@ -66,11 +66,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    uint64_t t0 = globaltimer_ns();
+    uint64_t t0 = 0;   // the timer is only consulted after 1024 failed (hardware-suspended) polls: ordinary waits never read it
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if ((++spins & 0x3ff) == 0) {
-            if (globaltimer_ns() - t0 > B2_WAIT_TIMEOUT_NS) {
+            const uint64_t now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > B2_WAIT_TIMEOUT_NS) {
                 printf("b2: mbarrier wait timeout (block %d,%d,%d thread %d parity %u)\n", blockIdx.x,
                        blockIdx.y, blockIdx.z, threadIdx.x, parity);
                 __trap();

@@ -141,6 +141,12 @@ def head_case():
     print(f"smallconv head 512x512 3->64: {timeit(lambda: ops.smallconv(fr, w, b, y, flags=1)):7.1f} us")
     x = rnd(1, 64, 64, 4); w2 = rnd(320, 4, 3, 3); b2 = torch.randn(320, device=dev); y2 = torch.empty(1, 64, 64, 320, device=dev, dtype=torch.float16)
     print(f"smallconv conv_in 64x64 4->320: {timeit(lambda: ops.smallconv(x, w2, b2, y2)):7.1f} us")
+if "attnbalance" in sys.argv:
+    for heads in [1, 2, 4, 5, 8, 9, 10]:
+        attn_case(1, heads, 4096)
+    for heads in [5, 10, 18, 20]:
+        attn_case(1, heads, 1024)
+    sys.exit(0)
 if "all" in sys.argv or len(sys.argv) == 1:
     gn_case(1, 64, 64, 320); gn_case(1, 64, 64, 640, 320); gn_case(1, 32, 32, 640); gn_case(1, 16, 16, 1280); gn_case(1, 8, 8, 1280, 1280)
     ln_case(4096, 320); ln_case(1024, 640); ln_case(256, 1280); ln_case(64, 1280)
