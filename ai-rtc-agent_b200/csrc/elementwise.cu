@@ -509,19 +509,40 @@ int groupnorm_launch(const GroupNormArgs& a, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------ LayerNorm
-__global__ void layernorm_kernel(const __half* __restrict__ x, int ldx, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, __half* __restrict__ y, int ldy, long rows,
-                                 int c, float eps) {
-    B2_PDL_ENTRY();
+// One warp per row; the row (<= 5 x 16 B per lane, C <= 1280) stays in registers between the statistics and the
+// normalisation, and gamma/beta (parameters, not produced by the previous kernel) are fetched before the PDL wait.
+constexpr int LN_MAXK = 5;
+__global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, int ldx, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, __half* __restrict__ y, int ldy, long rows,
+                                                        int c, float eps) {
     const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    const int chunks = c >> 3;
+    float4 g[LN_MAXK][2], bt[LN_MAXK][2];
+#pragma unroll
+    for (int k = 0; k < LN_MAXK; ++k) {
+        const int ch = lane + 32 * k;
+        if (ch < chunks) {
+            g[k][0] = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * ch);
+            g[k][1] = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * ch + 1);
+            bt[k][0] = __ldg(reinterpret_cast<const float4*>(beta) + 2 * ch);
+            bt[k][1] = __ldg(reinterpret_cast<const float4*>(beta) + 2 * ch + 1);
+        }
+    }
+    B2_PDL_ENTRY();
     if (row >= rows) return;
     const __half* xr = x + row * ldx;
-    const int chunks = c >> 3;
+    uint4 xv[LN_MAXK];
+#pragma unroll
+    for (int k = 0; k < LN_MAXK; ++k) {
+        const int ch = lane + 32 * k;
+        xv[k] = make_uint4(0, 0, 0, 0);
+        if (ch < chunks) xv[k] = reinterpret_cast<const uint4*>(xr)[ch];
+    }
     float s = 0.f, ss = 0.f;
-    for (int k = lane; k < chunks; k += 32) {
-        const uint4 u = reinterpret_cast<const uint4*>(xr)[k];
-        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int k = 0; k < LN_MAXK; ++k) {   // absent chunks are zero: they add nothing
+        const __half2* h = reinterpret_cast<const __half2*>(&xv[k]);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const float2 f = __half22float2(h[i]);
@@ -537,26 +558,29 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, int ldx, const fl
     const float mean = s / c;
     const float rstd = rsqrtf(fmaxf(ss / c - mean * mean, 0.f) + eps);
     __half* yr = y + row * ldy;
-    for (int k = lane; k < chunks; k += 32) {
-        const uint4 u = reinterpret_cast<const uint4*>(xr)[k];
-        const __half2* h = reinterpret_cast<const __half2*>(&u);
-        uint4 o;
-        __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float2 f = __half22float2(h[i]);
-            const int cc = k * 8 + 2 * i;
-            oh[i] = __floats2half2_rn((f.x - mean) * rstd * gamma[cc] + beta[cc],
-                                      (f.y - mean) * rstd * gamma[cc + 1] + beta[cc + 1]);
+    for (int k = 0; k < LN_MAXK; ++k) {
+        const int ch = lane + 32 * k;
+        if (ch < chunks) {
+            const __half2* h = reinterpret_cast<const __half2*>(&xv[k]);
+            const float* gp = reinterpret_cast<const float*>(&g[k][0]);
+            const float* bp = reinterpret_cast<const float*>(&bt[k][0]);
+            uint4 o;
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(h[i]);
+                oh[i] = __floats2half2_rn((f.x - mean) * rstd * gp[2 * i] + bp[2 * i], (f.y - mean) * rstd * gp[2 * i + 1] + bp[2 * i + 1]);
+            }
+            reinterpret_cast<uint4*>(yr)[ch] = o;
         }
-        reinterpret_cast<uint4*>(yr)[k] = o;
     }
 }
 
 int layernorm_launch(const __half* x, int ldx, const float* gamma, const float* beta, __half* y, int ldy,
                      long rows, int c, float eps, cudaStream_t s) {
-    if ((c & 7) || (ldx & 7) || (ldy & 7)) {
-        b2_set_error("layernorm: c/ld must be multiples of 8 (c=%d)", c);
+    if ((c & 7) || (ldx & 7) || (ldy & 7) || c > LN_MAXK * 256 || (reinterpret_cast<uintptr_t>(gamma) & 15) || (reinterpret_cast<uintptr_t>(beta) & 15)) {
+        b2_set_error("layernorm: c/ld must be multiples of 8, c <= %d, gamma/beta 16-byte aligned (c=%d)", LN_MAXK * 256, c);
         return -1;
     }
     const int wpb = 8;

@@ -454,12 +454,14 @@ struct b2sd_engine {
     int run(std::vector<Op>& ops, cudaStream_t s) {
         static const bool dbg = getenv("B200SD_DEBUG_SYNC") != nullptr;
         static const char* skip = getenv("B200SD_SKIP");  // debug: "groupnorm,attn" drops those launches (timing only)
+        static const char* skip_name = getenv("B200SD_SKIP_NAME");  // debug: drop launches whose label contains this substring
         int idx = 0;
         for (auto& op : ops) {
             if (skip) {
                 const std::string kind = op.name.substr(0, op.name.find(' '));
                 if (!kind.empty() && std::string(skip).find(kind) != std::string::npos) { ++idx; continue; }
             }
+            if (skip_name && op.name.find(skip_name) != std::string::npos) { ++idx; continue; }
             TRY(op(s));
             if (dbg) {
                 cudaError_t e = cudaStreamSynchronize(s);
