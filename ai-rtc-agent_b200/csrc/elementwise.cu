@@ -636,32 +636,37 @@ int smallconv_prep_launch(const __half* w_oihw, float* wt, int cout, int cin, cu
 }
 
 template <int CIN>
-__global__ void __launch_bounds__(128) smallconv_kernel(SmallConvArgs a) {
+__global__ void __launch_bounds__(128) smallconv_kernel(SmallConvArgs a, int G) {
     B2_PDL_ENTRY();
-    extern __shared__ float ws[];  // [CIN*9][64] weights of this CTA's channel group, then bias[64]
+    extern __shared__ float ws[];  // [CIN*9][G] weights of this CTA's G-channel output group, then bias[G]
     constexpr int K = CIN * 9;
     const int cout = a.cout;
-    const int cg = blockIdx.y;   // 64-channel output group
-    for (int i = threadIdx.x; i < K * 16; i += blockDim.x) {
-        const int k = i >> 4, j = i & 15;
-        reinterpret_cast<float4*>(ws)[i] = *reinterpret_cast<const float4*>(a.wt + (long)k * cout + cg * 64 + 4 * j);
+    const int cg = blockIdx.y;   // G-channel output group (G = 64, or 16 for small images: more CTAs)
+    const int gq = G >> 2;
+    for (int i = threadIdx.x; i < K * gq; i += blockDim.x) {
+        const int k = i / gq, j = i - k * gq;
+        reinterpret_cast<float4*>(ws)[i] = *reinterpret_cast<const float4*>(a.wt + (long)k * cout + cg * G + 4 * j);
     }
-    float* bs = ws + K * 64;
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) bs[i] = a.bias ? a.bias[cg * 64 + i] : 0.f;
+    float* bs = ws + K * G;
+    for (int i = threadIdx.x; i < G; i += blockDim.x) bs[i] = a.bias ? a.bias[cg * G + i] : 0.f;
     __syncthreads();
-    const long npix = (long)a.nb * a.h * a.w_;
-    for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long)gridDim.x * blockDim.x) {
-        const int xw = (int)(p % a.w_);
-        const int yh = (int)((p / a.w_) % a.h);
-        const int n = (int)(p / ((long)a.w_ * a.h));
+    const int npix = a.nb * a.h * a.w_;           // < 2^31 (checked by the launcher)
+    const bool same_size = a.in_h == a.h && a.in_w == a.w_;   // no resize: skip the per-tap integer divisions
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
+        const int xw = p % a.w_;
+        const int yh = (p / a.w_) % a.h;
+        const int n = p / (a.w_ * a.h);
         float patch[K];
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
             const int yy = yh + tap / 3 - 1, xx = xw + tap % 3 - 1;
             const bool in = (yy >= 0) && (yy < a.h) && (xx >= 0) && (xx < a.w_);
             // nearest resize (VaeImageProcessor.resize -> F.interpolate default mode): src = floor(dst*in/out)
-            const int sy = in ? (int)(((long)yy * a.in_h) / a.h) : 0;
-            const int sx = in ? (int)(((long)xx * a.in_w) / a.w_) : 0;
+            int sy = 0, sx = 0;
+            if (in) {
+                if (same_size) { sy = yy; sx = xx; }
+                else { sy = (int)(((long)yy * a.in_h) / a.h); sx = (int)(((long)xx * a.in_w) / a.w_); }
+            }
             const long base = (((long)n * a.in_h + sy) * a.in_w + sx) * CIN;
 #pragma unroll
             for (int c = 0; c < CIN; ++c) {
@@ -686,33 +691,38 @@ __global__ void __launch_bounds__(128) smallconv_kernel(SmallConvArgs a) {
                 patch[tap * CIN + c] = v;
             }
         }
-        float acc[64];
+        // 16 output channels per pass: the patch stays in registers, the accumulators are reused (64 at once needed
+        // ~240 registers per thread => 2 CTAs per SM and a latency-bound FMA stream)
+        __half* dst = a.y + (long)p * a.ldy + cg * G;
+#pragma unroll 1
+        for (int q = 0; q < G; q += 16) {
+            float acc[16];
 #pragma unroll
-        for (int o = 0; o < 64; ++o) acc[o] = bs[o];
+            for (int o = 0; o < 16; ++o) acc[o] = bs[q + o];
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float v = patch[k];
+            for (int k = 0; k < K; ++k) {
+                const float v = patch[k];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float4 w4 = *reinterpret_cast<const float4*>(ws + k * 64 + 4 * j);
-                acc[4 * j] += v * w4.x; acc[4 * j + 1] += v * w4.y; acc[4 * j + 2] += v * w4.z; acc[4 * j + 3] += v * w4.w;
-            }
-        }
-        __half* dst = a.y + p * a.ldy + cg * 64;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            uint4 u;
-            __half2* hh = reinterpret_cast<__half2*>(&u);
-#pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                float v0 = acc[8 * j + 2 * o], v1 = acc[8 * j + 2 * o + 1];
-                if (a.flags & SC_OUT_RELU) {
-                    v0 = fmaxf(v0, 0.f);
-                    v1 = fmaxf(v1, 0.f);
+                for (int j = 0; j < 4; ++j) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(ws + k * G + q + 4 * j);
+                    acc[4 * j] += v * w4.x; acc[4 * j + 1] += v * w4.y; acc[4 * j + 2] += v * w4.z; acc[4 * j + 3] += v * w4.w;
                 }
-                hh[o] = __floats2half2_rn(v0, v1);
             }
-            reinterpret_cast<uint4*>(dst)[j] = u;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                uint4 u;
+                __half2* hh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    float v0 = acc[8 * j + 2 * o], v1 = acc[8 * j + 2 * o + 1];
+                    if (a.flags & SC_OUT_RELU) {
+                        v0 = fmaxf(v0, 0.f);
+                        v1 = fmaxf(v1, 0.f);
+                    }
+                    hh[o] = __floats2half2_rn(v0, v1);
+                }
+                reinterpret_cast<uint4*>(dst + q)[j] = u;
+            }
         }
     }
 }
@@ -722,11 +732,16 @@ int smallconv_launch(const SmallConvArgs& a, cudaStream_t s) {
         b2_set_error("smallconv: cin %d cout %d unsupported (cout must be a multiple of 64; prepared weights required)", a.cin, a.cout);
         return -1;
     }
-    const size_t smem = ((size_t)a.cin * 9 * 64 + 64) * sizeof(float);
-    const int groups = a.cout / 64;
     const long npix = (long)a.nb * a.h * a.w_;
+    if (npix >= (1l << 31) - 128 * 148 * 32) {
+        b2_set_error("smallconv: %ld pixels exceed the 32-bit index range", npix);
+        return -1;
+    }
     long blocks = (npix + 127) / 128;
-    const long cap = (148 * 8 + groups - 1) / groups;
+    const int G = blocks * (a.cout / 64) < 148 * 4 ? 16 : 64;   // few pixels: narrower channel groups, more CTAs
+    const size_t smem = ((size_t)a.cin * 9 * G + G) * sizeof(float);
+    const int groups = a.cout / G;
+    const long cap = (148 * 16 + groups - 1) / groups;   // two full waves of 8 CTAs per SM; beyond that, grid-stride
     if (blocks > cap) blocks = cap;
     static bool attr = false;
     if (!attr) {
@@ -734,8 +749,8 @@ int smallconv_launch(const SmallConvArgs& a, cudaStream_t s) {
         cudaFuncSetAttribute(smallconv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         attr = true;
     }
-    if (a.cin == 3) B2_LAUNCHED("smallconv", launch_k(smallconv_kernel<3>, dim3((unsigned)blocks, groups), dim3(128), smem, s, 1, a));
-    else B2_LAUNCHED("smallconv", launch_k(smallconv_kernel<4>, dim3((unsigned)blocks, groups), dim3(128), smem, s, 1, a));
+    if (a.cin == 3) B2_LAUNCHED("smallconv", launch_k(smallconv_kernel<3>, dim3((unsigned)blocks, groups), dim3(128), smem, s, 1, a, G));
+    else B2_LAUNCHED("smallconv", launch_k(smallconv_kernel<4>, dim3((unsigned)blocks, groups), dim3(128), smem, s, 1, a, G));
     return 0;
 }
 
