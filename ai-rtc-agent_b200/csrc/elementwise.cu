@@ -429,10 +429,12 @@ static int gn_cluster_size(const GroupNormArgs& a) {
     if ((cpg & 1) || (a.ca & 1) || GNC_THREADS % (cpg >> 1) != 0 || (a.lda & 1) || (a.cb && (a.ldb & 1)) || (a.ldy & 1)) return 0;
     const long words = (long)a.hw * (cpg >> 1);
     const long cap = (long)GNC_THREADS * GNC_ITEMS;
+    static const char* mc = getenv("B2_GN_ITEMS");   // tuning: max half2 words per thread (default GNC_ITEMS)
+    const int max_items = mc ? atoi(mc) : GNC_ITEMS;
     for (int cl = 1; cl <= 8; cl <<= 1) {
         const int ppc = (a.hw + cl - 1) / cl;
         const int pstep = GNC_THREADS / (cpg >> 1);
-        if ((long)((ppc + pstep - 1) / pstep) <= GNC_ITEMS && words <= cap * cl) return cl;
+        if ((long)((ppc + pstep - 1) / pstep) <= max_items && words <= cap * cl) return cl;
     }
     return 0;
 }
