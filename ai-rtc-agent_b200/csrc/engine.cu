@@ -1200,6 +1200,62 @@ int b2sd_profile(b2sd_handle h, const void* frame_in, int in_h, int in_w, void* 
     return 0;
 }
 
+// Device time of one launch class inside a CUDA graph: every frame-program launch whose label starts with `kind`
+// ("igemm", "attn", "groupnorm", ...) is captured, in program order, into its own graph (same PDL edges, same buffers,
+// same weight streaming as the frame graph) and that graph is replayed `iters` times between two events.
+int b2sd_profile_kind(b2sd_handle h, const char* kind, int iters, double* ms_per_replay, int* launches, double* flops,
+                      void* stream) {
+    if (!h || !h->built || !kind || iters < 1 || !ms_per_replay) {
+        b2_set_error("b2sd_profile_kind: bad arguments");
+        return -1;
+    }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const std::string k(kind);
+    int n = 0;
+    double fl = 0.0;
+    for (auto& op : h->prog_frame)   // eager pass first: one-time attribute/driver-entry-point setup may not run under capture
+        if (op.name.compare(0, k.size(), k) == 0) { TRY(op(s)); ++n; fl += op.flops; }
+    CUDA_OK(cudaStreamSynchronize(s));
+    if (n == 0) {
+        b2_set_error("b2sd_profile_kind: no launch of kind '%s'", kind);
+        return -1;
+    }
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ge = nullptr;
+    cudaStream_t cs;   // the caller's stream may be the legacy default stream, which cannot capture
+    CUDA_OK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    int rc = 0;
+    for (auto& op : h->prog_frame)
+        if (op.name.compare(0, k.size(), k) == 0 && op(cs)) { rc = -1; break; }
+    cudaError_t ce = cudaStreamEndCapture(cs, &g);
+    cudaStreamDestroy(cs);
+    if (rc || ce != cudaSuccess) {
+        if (g) cudaGraphDestroy(g);
+        if (!rc) b2_set_error("b2sd_profile_kind: capture failed: %s", cudaGetErrorString(ce));
+        return -1;
+    }
+    CUDA_OK(cudaGraphInstantiate(&ge, g, 0));
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0));
+    CUDA_OK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) CUDA_OK(cudaGraphLaunch(ge, s));
+    CUDA_OK(cudaEventRecord(e0, s));
+    for (int i = 0; i < iters; ++i) CUDA_OK(cudaGraphLaunch(ge, s));
+    CUDA_OK(cudaEventRecord(e1, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaGraphExecDestroy(ge);
+    cudaGraphDestroy(g);
+    *ms_per_replay = (double)ms / iters;
+    if (launches) *launches = n;
+    if (flops) *flops = fl;
+    return 0;
+}
+
 int b2sd_launches_per_step(b2sd_handle h) { return h ? h->launches : 0; }
 
 }  // extern "C"

@@ -271,6 +271,15 @@ class StreamDiffusion:
                                           out.data_ptr(), iters, buf, len(buf), self._stream()), "b2sd_profile")
         return json.loads(buf.value.decode())
 
+    def profile_kind(self, kind: str, iters: int = 20):
+        """Device time of one launch class inside a CUDA graph (only those launches, program order):
+        {"ms": per replay, "launches": n, "flops": algorithmic FLOPs per replay}."""
+        self._check()
+        ms, n, fl = C.c_double(), C.c_int(), C.c_double()
+        capi.check(self._lib.b2sd_profile_kind(self._handle, kind.encode(), iters, C.byref(ms), C.byref(n), C.byref(fl),
+                                               self._stream()), "b2sd_profile_kind")
+        return {"ms": ms.value, "launches": n.value, "flops": fl.value}
+
     @property
     def launches_per_step(self) -> int:
         return self._lib.b2sd_launches_per_step(self._handle)

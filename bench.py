@@ -244,9 +244,11 @@ def main_gpu(args):
         d = by.setdefault(kind, {"ms": 0.0, "flops": 0.0, "launches": 0})
         d["ms"] += op["ms"]; d["flops"] += op["flops"]; d["launches"] += 1
     peaks, peak_src = measured_peaks()
-    ig = by.get("igemm", {"ms": 1e-9, "flops": 0.0, "launches": 0})
+    # dominant kernel: its launches alone, replayed from their own CUDA graph (same order, buffers, PDL edges and weight
+    # streaming as inside the frame graph) -> average launch duration without the host-side gaps of the eager replay
+    ig = stream.profile_kind("igemm", iters=20)
     ig_tflops = ig["flops"] / (ig["ms"] * 1e-3) / 1e12
-    eager_ms = sum(op["ms"] for op in prof)
+    step_ms = ms_total / args.steps
     step_tflops = GFLOP_PER_FRAME * (value / world) / 1e3
     traffic, traffic_note = None, "no ncu capture found under profiles/"
     tpath = os.path.join(ROOT, "profiles", "igemm_traffic.json")
@@ -260,11 +262,13 @@ def main_gpu(args):
         "frac": ig_tflops / peaks["bf16_tflops_sustained"], "traffic": traffic,
         "peak_source": peak_src + ", sustained figure (kernel timed inside a long step)",
         "traffic_note": traffic_note,
-        "kernel_share_of_step": ig["ms"] / eager_ms, "kernel_launches_per_step": ig["launches"],
+        "kernel_share_of_step": ig["ms"] / step_ms, "kernel_launches_per_step": ig["launches"],
+        "kernel_ms_per_step": ig["ms"], "kernel_avg_launch_us": 1e3 * ig["ms"] / max(ig["launches"], 1),
+        "kernel_timing": "CUDA events around a graph holding only the igemm launches of one frame, 20 replays",
         "kernel_algorithmic_gflop_per_step": ig["flops"] / 1e9,
         "step_achieved": step_tflops, "step_frac": step_tflops / peaks["bf16_tflops_sustained"],
         "step_algorithmic_gflop": GFLOP_PER_FRAME,
-        "by_kernel_ms": {k: round(v["ms"], 4) for k, v in sorted(by.items(), key=lambda kv: -kv[1]["ms"])},
+        "by_kernel_eager_ms": {k: round(v["ms"], 4) for k, v in sorted(by.items(), key=lambda kv: -kv[1]["ms"])},
     }
     # ---- CPU baseline (reported, not the target): bounded sample on this box's host cores
     cpu = None

@@ -166,6 +166,11 @@ int b2sd_get_tensor(b2sd_handle h, const char* name, void* dst, int64_t capacity
  * writes a JSON array [{"name","ms"},...] to json_buf.  Synchronises. */
 int b2sd_profile(b2sd_handle h, const void* frame_in, int in_h, int in_w, void* frame_out, int iters,
                  char* json_buf, int64_t cap, void* stream);
+/* Device time of one launch class ("igemm", "attn", "groupnorm", "layernorm", ...) of the frame program, measured by
+ * replaying a CUDA graph that holds only those launches (same order, buffers and weight streaming as the frame graph).
+ * ms_per_replay = average over `iters` replays; launches / flops (optional) = launches and algorithmic FLOPs per replay. */
+int b2sd_profile_kind(b2sd_handle h, const char* kind, int iters, double* ms_per_replay, int* launches, double* flops,
+                      void* stream);
 /* number of kernel launches (graph nodes) in one b2sd_step */
 int b2sd_launches_per_step(b2sd_handle h);
 

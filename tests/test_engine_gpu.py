@@ -113,6 +113,26 @@ def test_tiny_graph_equals_eager(cuda, monkeypatch):
         assert torch.equal(a, b)
 
 
+def test_tiny_profile_kind(cuda):
+    """b2sd_profile_kind replays one launch class from its own CUDA graph and leaves the stream state usable."""
+    from oracle import pipeline as opipe
+    from oracle import weights as ow
+    sd, orc = _build("tiny", True, [20], 128, cuda)
+    frame = ow.make_frame(128, 128, seed=3)
+    ref = opipe.frame_to_u8(orc, frame)
+    out0 = sd.step_u8(frame.to(cuda)).cpu()
+    r = sd.profile_kind("igemm", iters=3)
+    assert r["launches"] > 10 and r["ms"] > 0 and r["flops"] > 0
+    g = sd.profile_kind("groupnorm", iters=3)
+    assert g["launches"] > 0 and g["flops"] == 0
+    with pytest.raises(Exception):
+        sd.profile_kind("no-such-kind")
+    # T=1: no temporal state, the same frame must give the same output after the profiling replays
+    out1 = sd.step_u8(frame.to(cuda)).cpu()
+    assert torch.equal(out0, out1)
+    _u8_check(out1.to(cuda), ref, "frame after profile_kind")
+
+
 def test_tiny_update_prompt_and_t_index(cuda):
     """update_prompt refreshes the cross-attention K/V cache; update_t_index_list changes only the timestep
     embedding (lib/wrapper.py:389-407 quirk) -- both must track the oracle."""
