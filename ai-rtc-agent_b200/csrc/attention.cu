@@ -20,7 +20,7 @@ constexpr int AT_SM_THREADS = 256;
 // Softmax: a query row (TMEM lane) is shared by TWO threads (warps w and w+4 see the same lane quarter), each owning half
 // of the S columns / O columns.  One warp per scheduler was pure latency (tcgen05.ld -> max chain -> ex2 chain): measured
 // on B200, 288 CTAs (two per SM) took exactly as long as 128 (one per SM), so the second warp per scheduler is free.
-// The pair only exchanges its block maximum (fp16, 512 B of shared memory, one 64-thread named barrier per KV block);
+// The pair only exchanges its block maximum (fp16, 512 B of shared memory, two 64-thread named barriers per KV block);
 // the row sums stay private until the end.
 constexpr uint32_t AT_TMEM_COLS = 256;
 
@@ -219,12 +219,11 @@ __global__ void __launch_bounds__(AT_THREADS, (DA == 1 ? 2 : 1)) attn_kernel(con
             mbar_arrive(s_empty);
             const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
             // pair exchange in fp16, rounded UP so that exp2 arguments stay <= 0 (any common m is a valid softmax shift).
-            // Single buffer is race free: the partner reads before it arrives on s_empty(j), and this thread's next write
-            // happens after s_full(j+1), which needs every s_empty(j) arrival.
             const __half mh = __float2half_ru(fmaxf(mx, -60000.f));
             xmax[hf * AT_BQ + r] = mh;
             pair_sync();
             const float mpair = fmaxf(__half2float(mh), __half2float(xmax[(hf ^ 1) * AT_BQ + r]));
+            pair_sync();   // both halves have read: the single exchange buffer may be rewritten for the next block
             const float m_new = fmaxf(m_run, mpair * p.scale_log2);
             const float alpha = ex2_approx(m_run - m_new);
             if (j > 0) mbar_wait(o_done, (j - 1) & 1);  // PV(j-1) retired: P buffer + O are ours

@@ -1280,7 +1280,12 @@ int igemm_plan(const IgemmDesc& d, IgemmPlan* plan) {
     const size_t stage_bytes = (size_t)kpack * ((size_t)IG_BM * IG_BK * 2 + (size_t)BN * IG_BK * 2);
     // TMA latency under load is ~1.3 us (tools/timeline.py): throughput per SM = bytes in flight / latency.  With at
     // most ~1 CTA per SM take the whole shared memory for the ring; with many CTAs keep two co-resident instead.
-    const long total_ctas = (long)p.tiles_w * p.tiles_h * p.tiles_n * n_tiles * splits;
+    static const char* pc_env = getenv("B2_PERSIST_CTAS");   // tuning: resident CTAs of a persistent launch (default 2 per SM)
+    const int persist_ctas = pc_env ? atoi(pc_env) : 2 * 148;
+    const long all_tiles = (long)p.tiles_w * p.tiles_h * p.tiles_n * n_tiles;
+    static const bool no_persist_e = getenv("B2_NO_PERSIST") != nullptr;
+    const bool will_persist = !no_persist_e && splits == 1 && all_tiles > 2 * 148 && 2 * BN <= 512;
+    const long total_ctas = will_persist ? persist_ctas : all_tiles * splits;
     static const char* stage_env = getenv("B2_STAGE_KB");
     // <= 1 CTA per SM anyway: take (nearly) all the shared memory for the ring, the mainloop is TMA-latency bound
     const size_t ring_budget = stage_env ? (size_t)atoi(stage_env) * 1024 : (size_t)((total_ctas <= 148 ? 200 : 100) * 1024);
@@ -1311,7 +1316,7 @@ int igemm_plan(const IgemmDesc& d, IgemmPlan* plan) {
     int grid_x = m_tiles;
     p.acc_bufs = 1;
     if (!no_persist && splits == 1 && (long)m_tiles * n_tiles > 2 * 148 && 2 * BN <= 512) {
-        grid_x = (2 * 148) / n_tiles;
+        grid_x = persist_ctas / n_tiles;
         if (grid_x < 1) grid_x = 1;
         if (grid_x > m_tiles) grid_x = m_tiles;
         p.acc_bufs = 2;
