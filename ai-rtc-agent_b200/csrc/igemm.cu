@@ -1069,7 +1069,6 @@ static int plan_swap(const IgemmDesc& d, IgemmPlan* plan) {
     }
     p.swap = 1;
     { static const char* dm = getenv("B2_DBG_MODE"); p.dbg_mode = dm ? atoi(dm) : 0; }
-    p.kpack = 1;
     p.acc_bufs = 1;
     p.BN = BN;
     auto lg = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
@@ -1270,14 +1269,9 @@ int igemm_plan(const IgemmDesc& d, IgemmPlan* plan) {
         p.epi.flags |= IG_SPLITK;
     }
     // ---- pipeline depth / smem
-    static const char* kpack_env = getenv("B2_KPACK");
-    (void)kpack_env;
-    int kpack = 1;  // packing several k-blocks per stage was measured slower (shallower prefetch, longer MMA issue code)
-    if (kpack < 1) kpack = 1;
-    if (kpack > 4) kpack = 4;
-    while (kpack > 1 && p.kb_per_split < 2 * kpack) kpack >>= 1;
-    p.kpack = kpack;
-    const size_t stage_bytes = (size_t)kpack * ((size_t)IG_BM * IG_BK * 2 + (size_t)BN * IG_BK * 2);
+    // one K-block (64 channels of one tap) per pipeline stage: packing several per stage was measured slower (shallower
+    // prefetch, longer MMA issue code)
+    const size_t stage_bytes = (size_t)IG_BM * IG_BK * 2 + (size_t)BN * IG_BK * 2;
     // TMA latency under load is ~1.3 us (tools/timeline.py): throughput per SM = bytes in flight / latency.  With at
     // most ~1 CTA per SM take the whole shared memory for the ring; with many CTAs keep two co-resident instead.
     static const char* pc_env = getenv("B2_PERSIST_CTAS");   // tuning: resident CTAs of a persistent launch (default 2 per SM)
@@ -1292,7 +1286,7 @@ int igemm_plan(const IgemmDesc& d, IgemmPlan* plan) {
     int stages = (int)(ring_budget / stage_bytes);
     if (stages < 2) stages = 2;
     if (stages > IG_MAX_STAGES) stages = IG_MAX_STAGES;
-    if (stages > (p.kb_per_split + kpack - 1) / kpack) stages = (p.kb_per_split + kpack - 1) / kpack < 2 ? 2 : (p.kb_per_split + kpack - 1) / kpack;
+    if (stages > p.kb_per_split) stages = p.kb_per_split < 2 ? 2 : p.kb_per_split;
     p.num_stages = stages;
     size_t pipe_bytes = stages * stage_bytes;
     if (splits > 1) {

@@ -23,7 +23,7 @@ constexpr int IG_THREADS = 192;   // warp0: TMA, warp1: MMA + TMEM alloc, warps 
 enum : int {
     IG_RELU = 1,    // relu after bias/residual
     IG_GEGLU = 2,   // tile columns [0,BN/2) = value, [BN/2,BN) = gate; out = v * gelu_erf(g)
-    IG_SPLITK = 4,  // write fp32 partials, epilogue applied by igemm_finalize_kernel
+    IG_SPLITK = 4,  // set by the planner: K is split over a thread-block cluster, partial tiles are reduced through DSMEM
 };
 
 struct IgEpilogue {
@@ -55,13 +55,10 @@ struct IgemmParams {
     int BN;                       // UMMA N (multiple of 16, <= 256)
     int num_stages;
     int acc_bufs;                 // 1, or 2 when the launch is persistent over M tiles (double-buffered accumulator)
-    int kpack;                    // k-blocks per pipeline stage (one mbarrier round trip covers all of them)
     uint32_t a_bytes;             // TMA box bytes of one A tile
     uint32_t b_bytes;
     uint32_t tmem_cols;
     unsigned long long* dbg_ts;   // debug: 8 globaltimer stamps per CTA (null = off)
-    float* partial;               // [splits][rows_total][n_pad] fp32 (split-K only)
-    int* tile_counters;           // one int per (m tile, n tile), zero between launches (split-K only)
     int n_pad;
     int swap;                     // 1: weights on the M side (128 output channels per CTA), pixels on the N side
     int tw_log2, th_log2;         // swap mode: pixel-tile extents are powers of two
@@ -116,8 +113,8 @@ struct IgemmDesc {
     int swap;         // 1 = swapped orientation: D^T = W . X^T, BN pixels (64/128/256) on the N side, transposed store
     int splits;       // 0/1 = none
     unsigned long long* dbg_ts;  // optional per-CTA timeline (8 stamps per CTA)
-    float* partial;   // workspace for split-K (size splits*rows*n_pad floats)
-    int* tile_counters;  // >= m_tiles*n_tiles zero-initialised ints (self re-arming)
+    float* partial;   // unused since split-K moved into a cluster (kept for ABI stability; op-level entry: debug timeline)
+    int* tile_counters;  // unused (ABI stability)
     IgEpilogue epi;
 };
 
@@ -133,11 +130,11 @@ struct IgemmPlan {
 
 // Returns 0 on success; fills plan. Encodes TMA descriptors (host side, no launch).
 int igemm_plan(const IgemmDesc& d, IgemmPlan* plan);
-// Enqueue on stream (main kernel + split-K finalize if needed).
+// Enqueue on stream (one launch; split-K plans launch a thread-block cluster per output tile).
 int igemm_launch(const IgemmPlan& plan, cudaStream_t stream);
 // one-time function attributes / driver entry points (call outside stream capture)
 int igemm_init();
-// workspace floats needed for a split-K plan
+// legacy: workspace floats of the former global-memory split-K (no workspace is needed any more)
 size_t igemm_partial_floats(int splits, long rows_total, int n_valid);
 const char* b2_last_error();
 void b2_set_error(const char* fmt, ...);

@@ -52,8 +52,8 @@ typedef struct {
     int stride;        /* 1 or 2 */
     int nb, ho, wo;    /* output extents */
     int bn;            /* N tile, 0 = auto */
-    int splits;        /* split-K factor, <=1 = off */
-    void* partial;     /* fp32 workspace, b2sd_igemm_partial_floats() floats, when splits > 1 */
+    int splits;        /* split-K factor (1, 2, 4 or 8 K slices reduced inside a thread-block cluster), <=1 = off */
+    void* partial;     /* no workspace is needed (cluster split-K); optional int64 [ctas][8] debug timeline, else NULL */
     void* out;         /* fp16 [nb*ho*wo][ldc] */
     int ldc;
     const float* colbias;
@@ -67,7 +67,7 @@ typedef struct {
 } b2sd_igemm_desc;
 
 int b2sd_op_igemm(const b2sd_igemm_desc* d, void* stream);
-uint64_t b2sd_igemm_partial_floats(int splits, int64_t rows_total, int n_valid);
+uint64_t b2sd_igemm_partial_floats(int splits, int64_t rows_total, int n_valid);   /* legacy sizing helper, unused by the cluster split-K */
 
 /* Flash attention (self / cross) of BasicTransformerBlock.attn1 / attn2 (inside unet.engine).
  * q: [nb*sq][ldq], head h at columns [h*dp, (h+1)*dp); k likewise (batch b at row b*k_bstride, 0 = shared);
