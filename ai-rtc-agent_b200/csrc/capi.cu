@@ -19,12 +19,7 @@ static ActView to_view(const b2sd_act_view& v) {
     return a;
 }
 
-int b2sd_op_igemm(const b2sd_igemm_desc* d, void* stream) {
-    if (!d) {
-        b2_set_error("b2sd_op_igemm: null desc");
-        return -1;
-    }
-    IgemmDesc g{};
+static void to_igemm_desc(const b2sd_igemm_desc* d, IgemmDesc& g) {
     g.nseg = d->nseg;
     for (int s = 0; s < d->nseg && s < IG_MAX_SRC; ++s) {
         g.src[s] = to_view(d->src[s]);
@@ -50,9 +45,59 @@ int b2sd_op_igemm(const b2sd_igemm_desc* d, void* stream) {
     g.epi.res_scale = d->res_scale;
     g.epi.flags = d->flags & (IG_RELU | IG_GEGLU);
     g.epi.n_valid = d->n_valid;
+}
+
+int b2sd_op_igemm(const b2sd_igemm_desc* d, void* stream) {
+    if (!d) {
+        b2_set_error("b2sd_op_igemm: null desc");
+        return -1;
+    }
+    IgemmDesc g{};
+    to_igemm_desc(d, g);
     IgemmPlan plan;
     if (igemm_plan(g, &plan)) return -1;
     return igemm_launch(plan, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b2sd_igemm_plan_dry(const b2sd_igemm_desc* d, int autotile, int allow_swap, b2sd_igemm_plan_info* out) {
+    if (!d || !out) {
+        b2_set_error("b2sd_igemm_plan_dry: null argument");
+        return -1;
+    }
+    IgemmDesc g{};
+    to_igemm_desc(d, g);
+    g.dbg_ts = nullptr;
+    IgemmPlan plan;
+    igemm_set_dry_run(true);
+    const int rc = autotile ? igemm_autotile(g, allow_swap != 0, &plan) : igemm_plan(g, &plan);
+    igemm_set_dry_run(false);
+    if (rc) return -1;
+    const bool halo = plan.mode == 1;
+    out->mode = plan.mode;
+    out->swap = halo ? 0 : plan.p.swap;
+    out->bn = halo ? plan.c3.BN : plan.p.BN;
+    out->splits = plan.splits;
+    out->grid_x = (int)plan.grid.x; out->grid_y = (int)plan.grid.y; out->grid_z = (int)plan.grid.z;
+    out->num_stages = halo ? plan.c3.num_bstages : plan.p.num_stages;
+    out->acc_bufs = halo ? 1 : plan.p.acc_bufs;
+    out->total_kb = halo ? 0 : plan.p.total_kb;
+    out->kb_per_split = halo ? 0 : plan.p.kb_per_split;
+    out->tmem_cols = (int)(halo ? plan.c3.tmem_cols : plan.p.tmem_cols);
+    out->m_tiles = halo ? (int)plan.grid.x : plan.p.tiles_w * plan.p.tiles_h * plan.p.tiles_n;
+    out->smem_bytes = (int64_t)plan.smem;
+    out->rows_total = plan.rows_total;
+    return 0;
+}
+
+int b2sd_groupnorm_plan_dry(int ca, int cb, int groups, int hw, int* cluster, int* threads, int* pixels_per_cta) {
+    GroupNormArgs a{};
+    a.ca = ca; a.cb = cb; a.lda = ca; a.ldb = cb; a.ldy = ca + cb; a.groups = groups; a.hw = hw; a.nb = 1;
+    if (groups <= 0 || hw <= 0 || ca <= 0 || !cluster) {
+        b2_set_error("b2sd_groupnorm_plan_dry: bad arguments");
+        return -1;
+    }
+    *cluster = groupnorm_plan(a, threads, pixels_per_cta);
+    return 0;
 }
 
 uint64_t b2sd_igemm_partial_floats(int splits, int64_t rows_total, int n_valid) {

@@ -439,6 +439,13 @@ static int gn_cluster_size(const GroupNormArgs& a) {
     return 0;
 }
 
+int groupnorm_plan(const GroupNormArgs& a, int* threads, int* pixels_per_cta) {
+    const int cl = gn_cluster_size(a);
+    if (threads) *threads = cl ? GNC_THREADS : 0;
+    if (pixels_per_cta) *pixels_per_cta = cl ? (a.hw + cl - 1) / cl : 0;
+    return cl;
+}
+
 size_t groupnorm_partial_floats(int nb, int groups) { return (size_t)nb * GN_MAX_CHUNKS * groups * 2 + 64; }
 
 int groupnorm_launch(const GroupNormArgs& a, cudaStream_t s) {

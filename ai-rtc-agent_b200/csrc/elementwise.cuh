@@ -22,6 +22,9 @@ struct GroupNormArgs {
 // two launches: coalesced per-chunk statistics, then normalise (+SiLU); both fill the whole GPU
 int groupnorm_launch(const GroupNormArgs& a, cudaStream_t s);
 size_t groupnorm_partial_floats(int nb, int groups);
+// host-only: which kernel groupnorm_launch would use.  Returns the cluster size (1/2/4/8) and fills threads per CTA and
+// pixels per CTA for gn_cluster_kernel, or 0 when the whole-grid kernel is used.
+int groupnorm_plan(const GroupNormArgs& a, int* threads, int* pixels_per_cta);
 int groupnorm_last_launch_count();  // 1 (cooperative single launch) or 2, for the most recent call on this thread
 
 // LayerNorm over the last dim of [rows][c] fp16 (eps 1e-5, affine), one warp per row.

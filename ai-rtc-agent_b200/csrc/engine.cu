@@ -107,6 +107,95 @@ struct Op {
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------
+// Tile / split-K policy of the frame program (batch-1 driven; derived from the cold-weight sweep in
+// profiles/r01_tile_sweep.md, not from a model).  Fills `plan` for the chosen (BN, splits, orientation).
+// allow_swap: the caller is a UNet contraction (never TAESD / V^T / GEGLU).  Host-only: works in igemm dry-run mode.
+int igemm_autotile(IgemmDesc d, bool allow_swap, IgemmPlan* plan_out) {
+    IgemmPlan& plan = *plan_out;
+    const bool geglu = (d.epi.flags & IG_GEGLU) != 0;
+    const int n_gemm = geglu ? 2 * d.epi.n_valid : d.epi.n_valid;
+    static const bool swap_on = getenv("B2_SWAP") != nullptr, swap_off = getenv("B2_NO_SWAP") != nullptr;
+    static const bool tuned = getenv("B2_NO_TUNED_TILES") == nullptr;
+    int total_kb = 0;
+    for (int sidx = 0; sidx < d.nseg && sidx < IG_MAX_SRC; ++sidx) total_kb += d.ntap[sidx] * (d.src[sidx].C / IG_BK);
+    const long rows_all = (long)d.Nb * d.Ho * d.Wo;
+    // Swapped orientation by default only where it measured faster (tools/bench_op.py, cold weights): the 8x8 level,
+    // where a 128-pixel M tile would be half empty.  B2_SWAP=1 forces it for every eligible UNet contraction.
+    const bool swap_here = allow_swap && !geglu && d.epi.n_valid >= 128 && (d.epi.n_valid & 7) == 0 &&
+                           (swap_on || (!swap_off && tuned && rows_all <= 64 && total_kb >= 90));
+    if (swap_here) {
+        d.swap = 1;
+        d.BN = rows_all >= 256 ? 256 : (rows_all >= 128 ? 128 : 64);
+        d.splits = 1; d.partial = nullptr;
+        TRY(igemm_plan(d, &plan));
+        const long ctas = (long)plan.grid.x * plan.grid.y;
+        int max_by_k = plan.p.total_kb / 4;
+        if (max_by_k < 1) max_by_k = 1;
+        if (max_by_k > 8) max_by_k = 8;
+        int splits = 1;
+        while (splits * 2 <= max_by_k && ctas * splits * 2 <= 192) splits *= 2;
+        if (splits > 1) {
+            d.splits = splits;
+            TRY(igemm_plan(d, &plan));
+        }
+        return 0;
+    }
+    d.swap = 0;
+    if (tuned && !geglu && n_gemm % 160 == 0 && total_kb >= 40) {
+        // K-heavy contractions that cannot fill the GPU with 160-wide tiles alone (batch 1): wide tiles + cluster
+        // split-K beat 64-wide tiles (profiles/r01_tile_sweep.md: -10..-40 % per launch, weights streamed from HBM)
+        d.BN = 160; d.splits = 1; d.partial = nullptr;
+        TRY(igemm_plan(d, &plan));
+        const int m_tiles = plan.p.tiles_w * plan.p.tiles_h * plan.p.tiles_n;
+        const long tiles = (long)m_tiles * (n_gemm / 160);
+        int bn = 0, splits = 0;
+        if (tiles < 132) {
+            if (m_tiles >= 8) { bn = 160; splits = 4; }
+            else if (m_tiles >= 2 && n_gemm % 256 == 0 && total_kb >= 180) { bn = 256; splits = 8; }
+        }
+        if (bn) {
+            d.BN = bn; d.splits = splits;
+            TRY(igemm_plan(d, &plan));
+            return 0;
+        }
+    }
+    static const int cands[] = {256, 160, 128, 64, 32, 16};
+    std::vector<int> valid;
+    for (int bn : cands) {
+        if (geglu && (bn % 32 != 0 || bn < 64)) continue;
+        if (n_gemm % bn == 0) valid.push_back(bn);
+    }
+    if (valid.empty()) {  // ragged N: one masked tile size
+        int bn = 16;
+        while (bn < n_gemm && bn < 128) bn <<= 1;
+        valid.push_back(bn);
+    }
+    for (int bn : valid) {
+        if (bn < 64 && n_gemm >= 64) break;  // narrow tiles re-read A too often: prefer split-K below
+        d.BN = bn; d.splits = 1; d.partial = nullptr;
+        TRY(igemm_plan(d, &plan));
+        if ((long)plan.grid.x * plan.grid.y >= 132) return 0;
+    }
+    // not enough tiles for one wave: smallest reasonable tile, then split K
+    int bn = valid.back();
+    for (int v : valid) if (v >= 64) bn = v;  // smallest >= 64 if any (valid is descending)
+    d.BN = bn; d.splits = 1; d.partial = nullptr;
+    TRY(igemm_plan(d, &plan));
+    const long ctas = (long)plan.grid.x * plan.grid.y;
+    int splits = ctas >= 96 ? 1 : (int)((148 + ctas - 1) / ctas);
+    if (tuned && ctas >= 64 && total_kb <= 12) splits = 1;   // the cluster reduction (~3 us) costs more than 5 k-blocks
+    const int max_by_k = plan.p.total_kb / 4 > 0 ? plan.p.total_kb / 4 : 1;
+    if (splits > max_by_k) splits = max_by_k;
+    if (splits > 8) splits = 8;
+    if (geglu) splits = 1;
+    if (splits > 1) {
+        d.splits = splits;
+        TRY(igemm_plan(d, &plan));
+    }
+    return 0;
+}
+
 struct b2sd_engine {
     b2sd_config cfg{};
     int lh = 0, lw = 0;  // latent extents
@@ -261,113 +350,17 @@ struct b2sd_engine {
     static ActView view(const Act& a) { return ActView{a.p, a.n, a.h, a.w, a.c, a.ld}; }
     static ActView tokens(const Act& a) { return ActView{a.p, 1, 1, a.n * a.h * a.w, a.c, a.ld}; }
 
-    // choose N tile / split-K for a good grid, plan, and append the launch
+    // choose N tile / split-K for a good grid (igemm_autotile), plan, and append the launch
     int add_igemm(std::vector<Op>& dst, IgemmDesc d) {
         const bool geglu = (d.epi.flags & IG_GEGLU) != 0;
         const int n_gemm = geglu ? 2 * d.epi.n_valid : d.epi.n_valid;
-        static const bool swap_on = getenv("B2_SWAP") != nullptr, swap_off = getenv("B2_NO_SWAP") != nullptr;
-        static const bool tuned = getenv("B2_NO_TUNED_TILES") == nullptr;
-        int total_kb = 0;
-        for (int sidx = 0; sidx < d.nseg; ++sidx) total_kb += d.ntap[sidx] * (d.src[sidx].C / IG_BK);
-        const long rows_all = (long)d.Nb * d.Ho * d.Wo;
-        // Swapped orientation by default only where it measured faster (tools/bench_op.py, cold weights): the 8x8 level,
-        // where a 128-pixel M tile would be half empty.  B2_SWAP=1 forces it for every eligible UNet contraction.
-        const bool swap_here = allow_swap && !geglu && d.epi.n_valid >= 128 && (d.epi.n_valid & 7) == 0 &&
-                               (swap_on || (!swap_off && tuned && rows_all <= 64 && total_kb >= 90));
-        if (swap_here) {
-            IgemmPlan plan;
-            const long rows = (long)d.Nb * d.Ho * d.Wo;
-            d.swap = 1;
-            d.BN = rows >= 256 ? 256 : (rows >= 128 ? 128 : 64);
-            d.splits = 1; d.partial = nullptr;
-            TRY(igemm_plan(d, &plan));
-            const long ctas = (long)plan.grid.x * plan.grid.y;
-            int max_by_k = plan.p.total_kb / 4;
-            if (max_by_k < 1) max_by_k = 1;
-            if (max_by_k > 8) max_by_k = 8;
-            int splits = 1;
-            while (splits * 2 <= max_by_k && ctas * splits * 2 <= 192) splits *= 2;
-            if (splits > 1) {
-                d.splits = splits;
-                TRY(igemm_plan(d, &plan));
-            }
-            launches += 1;
-            char label[256];
-            snprintf(label, sizeof(label), "igemm %s rows=%ld n=%d kb=%d bn=%d splits=%d grid=%u,%u,%u swapped", cur.c_str(),
-                     plan.rows_total, d.epi.n_valid, plan.p.total_kb, plan.p.BN, plan.splits, plan.grid.x, plan.grid.y, plan.grid.z);
-            dst.push_back(Op([plan](cudaStream_t s) { return igemm_launch(plan, s); }, label,
-                             2.0 * (double)plan.rows_total * n_gemm * plan.p.total_kb * IG_BK));
-            return 0;
-        }
-        static const int cands[] = {256, 160, 128, 64, 32, 16};
-        int best_bn = 0;
         IgemmPlan plan;
-        if (tuned && !geglu && n_gemm % 160 == 0 && total_kb >= 40) {
-            // K-heavy contractions that cannot fill the GPU with 160-wide tiles alone (batch 1): wide tiles + cluster
-            // split-K beat 64-wide tiles (profiles/r01_tile_sweep.md: -10..-40 % per launch, weights streamed from HBM)
-            d.BN = 160; d.splits = 1; d.partial = nullptr;
-            TRY(igemm_plan(d, &plan));
-            const int m_tiles = plan.p.tiles_w * plan.p.tiles_h * plan.p.tiles_n;
-            const long tiles = (long)m_tiles * (n_gemm / 160);
-            int bn = 0, splits = 0;
-            if (tiles < 132) {
-                if (m_tiles >= 8) { bn = 160; splits = 4; }
-                else if (m_tiles >= 2 && n_gemm % 256 == 0 && total_kb >= 180) { bn = 256; splits = 8; }
-            }
-            if (bn) {
-                d.BN = bn; d.splits = splits;
-                TRY(igemm_plan(d, &plan));
-                best_bn = -1;   // planned
-            }
-        }
-        if (best_bn < 0) {
-            launches += 1;
-            char label[256];
-            snprintf(label, sizeof(label), "igemm %s rows=%ld n=%d kb=%d bn=%d splits=%d grid=%u,%u,%u taps", cur.c_str(),
-                     plan.rows_total, d.epi.n_valid, plan.p.total_kb, plan.p.BN, plan.splits, plan.grid.x, plan.grid.y, plan.grid.z);
-            dst.push_back(Op([plan](cudaStream_t s) { return igemm_launch(plan, s); }, label,
-                             2.0 * (double)plan.rows_total * n_gemm * plan.p.total_kb * IG_BK));
-            return 0;
-        }
-        std::vector<int> valid;
-        for (int bn : cands) {
-            if (geglu && (bn % 32 != 0 || bn < 64)) continue;
-            if (n_gemm % bn == 0) valid.push_back(bn);
-        }
-        if (valid.empty()) {  // ragged N: one masked tile size
-            int bn = 16;
-            while (bn < n_gemm && bn < 128) bn <<= 1;
-            valid.push_back(bn);
-        }
-        for (int bn : valid) {
-            if (bn < 64 && n_gemm >= 64) break;  // narrow tiles re-read A too often: prefer split-K below
-            d.BN = bn; d.splits = 1; d.partial = nullptr;
-            TRY(igemm_plan(d, &plan));
-            if ((long)plan.grid.x * plan.grid.y >= 132) { best_bn = bn; break; }
-        }
-        if (!best_bn) {
-            // not enough tiles for one wave: smallest reasonable tile, then split K
-            int bn = valid.back();
-            for (int v : valid) if (v >= 64) bn = v;  // smallest >= 64 if any (valid is descending)
-            d.BN = bn; d.splits = 1; d.partial = nullptr;
-            TRY(igemm_plan(d, &plan));
-            const long ctas = (long)plan.grid.x * plan.grid.y;
-            int splits = ctas >= 96 ? 1 : (int)((148 + ctas - 1) / ctas);
-            if (tuned && ctas >= 64 && total_kb <= 12) splits = 1;   // the cluster reduction (~3 us) costs more than 5 k-blocks
-            const int max_by_k = plan.p.total_kb / 4 > 0 ? plan.p.total_kb / 4 : 1;
-            if (splits > max_by_k) splits = max_by_k;
-            if (splits > 8) splits = 8;
-            if (geglu) splits = 1;
-            if (splits > 1) {
-                d.splits = splits;
-                TRY(igemm_plan(d, &plan));
-            }
-        }
+        TRY(igemm_autotile(d, allow_swap, &plan));
         launches += 1;
         char label[256];
         snprintf(label, sizeof(label), "igemm %s rows=%ld n=%d kb=%d bn=%d splits=%d grid=%u,%u,%u %s", cur.c_str(),
                  plan.rows_total, d.epi.n_valid, plan.p.total_kb, plan.p.BN, plan.splits, plan.grid.x, plan.grid.y,
-                 plan.grid.z, plan.mode == 1 ? (plan.c3.MT == 2 ? "halo16x16" : "halo16x8") : "taps");
+                 plan.grid.z, plan.p.swap ? "swapped" : (plan.mode == 1 ? (plan.c3.MT == 2 ? "halo16x16" : "halo16x8") : "taps"));
         dst.push_back(Op([plan](cudaStream_t s) { return igemm_launch(plan, s); }, label,
                          2.0 * (double)plan.rows_total * n_gemm * plan.p.total_kb * IG_BK));
         return 0;

@@ -939,8 +939,13 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     return fn;
 }
 
+// Planning without a GPU (tests of the host logic, b2sd_igemm_plan_dry): the tensor maps are left zeroed.
+static thread_local bool g_plan_dry = false;
+void igemm_set_dry_run(bool on) { g_plan_dry = on; }
+
 static int encode_act_map(CUtensorMap* m, const ActView& a, int box_c, int box_w, int box_h, int box_n,
                           int estride) {
+    if (g_plan_dry) return 0;
     auto enc = get_encode();
     if (!enc) return -1;
     cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.N};
@@ -961,6 +966,7 @@ static int encode_act_map(CUtensorMap* m, const ActView& a, int box_c, int box_w
 }
 
 static int encode_w_map(CUtensorMap* m, const __half* w, int rows, int ld, int box_rows) {
+    if (g_plan_dry) return 0;
     auto enc = get_encode();
     if (!enc) return -1;
     cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};

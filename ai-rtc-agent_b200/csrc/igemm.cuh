@@ -132,6 +132,9 @@ struct IgemmPlan {
 int igemm_plan(const IgemmDesc& d, IgemmPlan* plan);
 // Enqueue on stream (one launch; split-K plans launch a thread-block cluster per output tile).
 int igemm_launch(const IgemmPlan& plan, cudaStream_t stream);
+// dry run (this thread): igemm_plan computes tiling, grid, shared memory, pipeline depth but encodes no TMA descriptor,
+// so it works on a machine without a GPU driver (host-logic tests)
+void igemm_set_dry_run(bool on);
 // one-time function attributes / driver entry points (call outside stream capture)
 int igemm_init();
 // legacy: workspace floats of the former global-memory split-K (no workspace is needed any more)
@@ -140,3 +143,7 @@ const char* b2_last_error();
 void b2_set_error(const char* fmt, ...);
 
 }  // namespace b2
+
+// Tile / split-K policy of the frame program (engine.cu): picks BN, split-K factor and orientation for one contraction and
+// fills `plan`.  Host-only logic; combine with igemm_set_dry_run(true) to evaluate it without a GPU.
+int igemm_autotile(b2::IgemmDesc d, bool allow_swap, b2::IgemmPlan* plan);

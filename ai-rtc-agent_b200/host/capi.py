@@ -33,6 +33,16 @@ class IgemmDesc(C.Structure):
     ]
 
 
+class IgemmPlanInfo(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int), ("swap", C.c_int), ("bn", C.c_int), ("splits", C.c_int),
+        ("grid_x", C.c_int), ("grid_y", C.c_int), ("grid_z", C.c_int),
+        ("num_stages", C.c_int), ("acc_bufs", C.c_int), ("total_kb", C.c_int), ("kb_per_split", C.c_int),
+        ("tmem_cols", C.c_int), ("m_tiles", C.c_int),
+        ("smem_bytes", C.c_int64), ("rows_total", C.c_int64),
+    ]
+
+
 class AttnDesc(C.Structure):
     _fields_ = [
         ("q", C.c_void_p), ("ldq", C.c_int),
@@ -73,6 +83,10 @@ def lib() -> C.CDLL:
         _lib.b2sd_version.restype = C.c_int
         _lib.b2sd_op_igemm.argtypes = [C.POINTER(IgemmDesc), C.c_void_p]
         _lib.b2sd_op_igemm.restype = C.c_int
+        _lib.b2sd_igemm_plan_dry.argtypes = [C.POINTER(IgemmDesc), C.c_int, C.c_int, C.POINTER(IgemmPlanInfo)]
+        _lib.b2sd_igemm_plan_dry.restype = C.c_int
+        _lib.b2sd_groupnorm_plan_dry.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        _lib.b2sd_groupnorm_plan_dry.restype = C.c_int
         _lib.b2sd_igemm_partial_floats.argtypes = [C.c_int, C.c_int64, C.c_int]
         _lib.b2sd_igemm_partial_floats.restype = C.c_uint64
         vp, ci, cf, i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64

@@ -67,6 +67,26 @@ typedef struct {
 } b2sd_igemm_desc;
 
 int b2sd_op_igemm(const b2sd_igemm_desc* d, void* stream);
+
+/* Host-only planning (no GPU, no driver call): what b2sd_op_igemm (autotile = 0: the descriptor's bn / splits / swap as
+ * given) or the engine's tile policy (autotile = 1; allow_swap = the contraction may use the swapped orientation) would
+ * launch for this contraction.  Pointers in the descriptor only need plausible alignment.  For tests of the host logic. */
+typedef struct {
+    int mode;          /* 0 igemm_kernel, 1 conv3_kernel (halo reuse, opt-in) */
+    int swap, bn, splits;
+    int grid_x, grid_y, grid_z;
+    int num_stages;    /* operand ring depth */
+    int acc_bufs;      /* 2 = persistent over M tiles (double-buffered TMEM accumulator) */
+    int total_kb, kb_per_split;   /* K in 64-channel blocks, per cluster rank */
+    int tmem_cols;
+    int m_tiles;       /* 128-row output tiles */
+    int64_t smem_bytes, rows_total;
+} b2sd_igemm_plan_info;
+int b2sd_igemm_plan_dry(const b2sd_igemm_desc* d, int autotile, int allow_swap, b2sd_igemm_plan_info* out);
+
+/* Host-only: launch shape of GroupNorm over [ca | cb] channels, hw pixels per image: cluster = CTAs per (image, group) of the
+ * cluster kernel (0 = whole-grid cooperative kernel), threads per CTA, pixels per CTA. */
+int b2sd_groupnorm_plan_dry(int ca, int cb, int groups, int hw, int* cluster, int* threads, int* pixels_per_cta);
 uint64_t b2sd_igemm_partial_floats(int splits, int64_t rows_total, int n_valid);   /* legacy sizing helper, unused by the cluster split-K */
 
 /* Flash attention (self / cross) of BasicTransformerBlock.attn1 / attn2 (inside unet.engine).
