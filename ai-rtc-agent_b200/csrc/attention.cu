@@ -735,7 +735,7 @@ static size_t attn_smem_bytes(int da, int bkv) {
 }
 
 int attn_plan(const AttnDesc& d, AttnPlan* plan) {
-    memset(plan, 0, sizeof(*plan));
+    *plan = AttnPlan{};
     if (d.dp != 64 && d.dp != 128 && d.dp != 192) {
         b2_set_error("attn: padded head dim %d unsupported", d.dp);
         return -1;

@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
     const int ntile = blockIdx.y;
     const int kb_begin = blockIdx.z * p.kb_per_split;
     const int kb_end = min(p.total_kb, kb_begin + p.kb_per_split);
-    unsigned long long* ts = p.dbg_ts ? p.dbg_ts + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
+    [[maybe_unused]] unsigned long long* ts = p.dbg_ts ? p.dbg_ts + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
     B2_TS(if (ts && threadIdx.x == 0) ts[0] = globaltimer_ns();)
 
     if (warp == 0 && lane == 0) {
@@ -679,7 +679,7 @@ __global__ void __launch_bounds__(C3_THREADS) conv3_kernel(const __grid_constant
     const int ntile = blockIdx.y;
     const int u_begin = blockIdx.z * p.units_per_split;
     const int u_end = min(p.units_total, u_begin + p.units_per_split);
-    unsigned long long* ts = p.dbg_ts ? p.dbg_ts + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
+    [[maybe_unused]] unsigned long long* ts = p.dbg_ts ? p.dbg_ts + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
     B2_TS(if (ts && threadIdx.x == 0) ts[0] = globaltimer_ns();)
 
     if (warp == 0 && lane == 0) {
@@ -1164,7 +1164,7 @@ static int plan_swap(const IgemmDesc& d, IgemmPlan* plan) {
 }
 
 int igemm_plan(const IgemmDesc& d, IgemmPlan* plan) {
-    memset(plan, 0, sizeof(*plan));
+    *plan = IgemmPlan{};
     if (d.swap) return plan_swap(d, plan);
     IgemmParams& p = plan->p;
     if (d.nseg < 1 || d.nseg > IG_MAX_SRC) {
