@@ -65,10 +65,10 @@ def _check(info, d, total_kb, geglu=False):
             assert info.grid_x == info.m_tiles
 
 
-def _unet_shapes(chs, nb):
-    """(h, srcs, cout, stride, geglu, allow_swap) of every contraction family of a UNet with block channels `chs` at 64x64 latents"""
+def _unet_shapes(chs, nb, latent=64):
+    """(h, srcs, cout, stride, geglu, allow_swap) of every contraction family of a UNet with block channels `chs`"""
     out = []
-    res = [64, 32, 16, 8]
+    res = [latent, latent // 2, latent // 4, latent // 8]
     for lvl, (c, r) in enumerate(zip(chs, res)):
         cin_prev = chs[max(lvl - 1, 0)]
         out += [(r, [(cin_prev, 9)], c, 1, False, True), (r, [(c, 9)], c, 1, False, True),          # resnet conv1 / conv2
@@ -83,11 +83,13 @@ def _unet_shapes(chs, nb):
     return [(nb,) + s for s in out]
 
 
-@pytest.mark.parametrize("nb", [1, 4])
-def test_autotile_invariants_over_the_frame_program(nb):
-    shapes = _unet_shapes([320, 640, 1280, 1280], nb)
-    shapes += [(nb, r, [(64, 9)], 64, 1, False, False) for r in (512, 256, 128, 64)]                     # TAESD body
-    shapes += [(nb, r, [(64, 9)], 64, 2, False, False) for r in (512, 256, 128)]
+@pytest.mark.parametrize("nb,latent", [(1, 64), (4, 64), (4, 96), (1, 32)])
+def test_autotile_invariants_over_the_frame_program(nb, latent):
+    """BASELINE.json configs: 512x512 at stream batch 1 / 4, 768x768 at batch 4, 256x256 at batch 1"""
+    shapes = _unet_shapes([320, 640, 1280, 1280], nb, latent)
+    px = latent * 8
+    shapes += [(1, r, [(64, 9)], 64, 1, False, False) for r in (px, px // 2, px // 4, px // 8)]          # TAESD body (one frame)
+    shapes += [(1, r, [(64, 9)], 64, 2, False, False) for r in (px, px // 2, px // 4)]
     for (b, r, srcs, cout, stride, geglu, allow_swap) in shapes:
         d, kb = _desc(b, r, r, srcs, cout, stride=stride, geglu=geglu)
         info = _plan(d, 1, int(allow_swap))
