@@ -4,6 +4,7 @@
 #include "attention.cuh"
 #include "elementwise.cuh"
 #include "igemm.cuh"
+#include "tconv.cuh"
 
 using namespace b2;
 
@@ -43,7 +44,7 @@ static void to_igemm_desc(const b2sd_igemm_desc* d, IgemmDesc& g) {
     g.epi.ldr = d->ldr;
     g.epi.acc_scale = d->acc_scale;
     g.epi.res_scale = d->res_scale;
-    g.epi.flags = d->flags & (IG_RELU | IG_GEGLU);
+    g.epi.flags = d->flags & (IG_RELU | IG_GEGLU | IG_CONST_A | IG_CONST_B);
     g.epi.n_valid = d->n_valid;
 }
 
@@ -54,6 +55,11 @@ int b2sd_op_igemm(const b2sd_igemm_desc* d, void* stream) {
     }
     IgemmDesc g{};
     to_igemm_desc(d, g);
+    if (d->flags & B2SD_IG_TCONV) {   // the persistent halo-tile kernel (64 -> 64 channel 3x3 convolutions)
+        TconvPlan tp;
+        if (tconv_plan(g, &tp)) return -1;
+        return tconv_launch(tp, reinterpret_cast<cudaStream_t>(stream));
+    }
     IgemmPlan plan;
     if (igemm_plan(g, &plan)) return -1;
     return igemm_launch(plan, reinterpret_cast<cudaStream_t>(stream));
@@ -72,18 +78,17 @@ int b2sd_igemm_plan_dry(const b2sd_igemm_desc* d, int autotile, int allow_swap, 
     const int rc = autotile ? igemm_autotile(g, allow_swap != 0, &plan) : igemm_plan(g, &plan);
     igemm_set_dry_run(false);
     if (rc) return -1;
-    const bool halo = plan.mode == 1;
     out->mode = plan.mode;
-    out->swap = halo ? 0 : plan.p.swap;
-    out->bn = halo ? plan.c3.BN : plan.p.BN;
+    out->swap = plan.p.swap;
+    out->bn = plan.p.BN;
     out->splits = plan.splits;
     out->grid_x = (int)plan.grid.x; out->grid_y = (int)plan.grid.y; out->grid_z = (int)plan.grid.z;
-    out->num_stages = halo ? plan.c3.num_bstages : plan.p.num_stages;
-    out->acc_bufs = halo ? 1 : plan.p.acc_bufs;
-    out->total_kb = halo ? 0 : plan.p.total_kb;
-    out->kb_per_split = halo ? 0 : plan.p.kb_per_split;
-    out->tmem_cols = (int)(halo ? plan.c3.tmem_cols : plan.p.tmem_cols);
-    out->m_tiles = halo ? (int)plan.grid.x : plan.p.tiles_w * plan.p.tiles_h * plan.p.tiles_n;
+    out->num_stages = plan.p.num_stages;
+    out->acc_bufs = plan.p.acc_bufs;
+    out->total_kb = plan.p.total_kb;
+    out->kb_per_split = plan.p.kb_per_split;
+    out->tmem_cols = (int)plan.p.tmem_cols;
+    out->m_tiles = plan.p.tiles_w * plan.p.tiles_h * plan.p.tiles_n;
     out->smem_bytes = (int64_t)plan.smem;
     out->rows_total = plan.rows_total;
     return 0;

@@ -11,6 +11,7 @@
 
 #include <functional>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -18,6 +19,7 @@
 #include "attention.cuh"
 #include "elementwise.cuh"
 #include "igemm.cuh"
+#include "tconv.cuh"
 
 using namespace b2;
 
@@ -100,6 +102,9 @@ struct Op {
     std::function<int(cudaStream_t)> fn;
     std::string name;
     double flops = 0.0;  // algorithmic 2*MAC count of the launch (0 for non-contraction kernels)
+    std::shared_ptr<IgemmPlan> ig;   // contraction launches: the plan the closure launches (patched after the build: L2 prefetch chain)
+    const void* wptr = nullptr;      // its constant (weight) operand, for the predecessor's L2 prefetch
+    size_t wbytes = 0;
     template <class F>
     Op(F f, std::string n = "", double fl = 0.0) : fn(std::move(f)), name(std::move(n)), flops(fl) {}
     int operator()(cudaStream_t s) const { return fn(s); }
@@ -217,9 +222,7 @@ struct b2sd_engine {
     float* temb_h = nullptr;   // [B][4*C0]
     float* temb = nullptr;     // [B][4*C0]
     float* gn_ws = nullptr;    // GroupNorm chunk partials (shared: launches are stream-ordered)
-    float* splitk_ws = nullptr;
     int* tile_counters = nullptr;
-    size_t splitk_floats = 0;
     float coef_host[4][64]{};
 
     std::vector<Op> prog_frame, prog_prompt, prog_time;
@@ -351,19 +354,57 @@ struct b2sd_engine {
     static ActView tokens(const Act& a) { return ActView{a.p, 1, 1, a.n * a.h * a.w, a.c, a.ld}; }
 
     // choose N tile / split-K for a good grid (igemm_autotile), plan, and append the launch
+    // append a planned contraction; remembers its constant operand so the previous contraction can prefetch it into L2
+    void push_igemm(std::vector<Op>& dst, const IgemmPlan& plan, const IgemmDesc& d, const std::string& label, double flops) {
+        auto sp = std::make_shared<IgemmPlan>(plan);
+        Op op([sp](cudaStream_t s) { return igemm_launch(*sp, s); }, label, flops);
+        op.ig = sp;
+        if (d.epi.flags & IG_CONST_A) {
+            op.wptr = d.src[0].ptr;
+            op.wbytes = (size_t)d.src[0].N * d.src[0].H * d.src[0].W * d.src[0].ld * 2;
+        } else if (d.epi.flags & IG_CONST_B) {
+            op.wptr = d.w;
+            op.wbytes = (size_t)d.w_rows * d.w_ld * 2;
+        }
+        if (&dst == &prog_frame) launches += 1;
+        dst.push_back(std::move(op));
+    }
+
+    // choose N tile / split-K for a good grid (igemm_autotile), plan, and append the launch.  Every contraction of the
+    // engine has a packed weight matrix as its `w` operand unless the caller marked the activation view as the constant one.
     int add_igemm(std::vector<Op>& dst, IgemmDesc d) {
+        static const bool no_early = getenv("B2_NO_EARLY") != nullptr;
+        if (no_early) d.epi.flags &= ~(IG_CONST_A | IG_CONST_B);
+        else if (!(d.epi.flags & IG_CONST_A)) d.epi.flags |= IG_CONST_B;
         const bool geglu = (d.epi.flags & IG_GEGLU) != 0;
         const int n_gemm = geglu ? 2 * d.epi.n_valid : d.epi.n_valid;
         IgemmPlan plan;
         TRY(igemm_autotile(d, allow_swap, &plan));
-        launches += 1;
         char label[256];
         snprintf(label, sizeof(label), "igemm %s rows=%ld n=%d kb=%d bn=%d splits=%d grid=%u,%u,%u %s", cur.c_str(),
                  plan.rows_total, d.epi.n_valid, plan.p.total_kb, plan.p.BN, plan.splits, plan.grid.x, plan.grid.y,
-                 plan.grid.z, plan.p.swap ? "swapped" : (plan.mode == 1 ? (plan.c3.MT == 2 ? "halo16x16" : "halo16x8") : "taps"));
-        dst.push_back(Op([plan](cudaStream_t s) { return igemm_launch(plan, s); }, label,
-                         2.0 * (double)plan.rows_total * n_gemm * plan.p.total_kb * IG_BK));
+                 plan.grid.z, plan.p.swap ? "swapped" : "taps");
+        push_igemm(dst, plan, d, label, 2.0 * (double)plan.rows_total * n_gemm * plan.p.total_kb * IG_BK);
         return 0;
+    }
+
+    // Chain the L2 prefetch: contraction i pulls the weights of contraction i+1 (the last one those of the first: next frame).
+    void link_weight_prefetch(std::vector<Op>& ops) {
+        static const bool off = getenv("B2_NO_L2PF") != nullptr;
+        static const char* cap_env = getenv("B2_L2PF_MAX_MB");
+        const size_t cap = (size_t)(cap_env ? atoi(cap_env) : 64) << 20;
+        std::vector<Op*> ig;
+        for (auto& op : ops)
+            if (op.ig) ig.push_back(&op);
+        for (size_t i = 0; i < ig.size(); ++i) {
+            const Op* nxt = ig[(i + 1) % ig.size()];
+            IgemmPlan& pl = *ig[i]->ig;
+            pl.p.pf_ptr = nullptr;
+            pl.p.pf_bytes = 0;
+            if (off || !nxt->wptr || nxt->wbytes == 0 || nxt->wbytes > cap || pl.mode != 0) continue;
+            pl.p.pf_ptr = nxt->wptr;
+            pl.p.pf_bytes = nxt->wbytes & ~(size_t)15;
+        }
     }
 
     int add_groupnorm(const Act& xa, const Act* xb, const std::string& prefix, const Act& y, float eps, int silu) {
@@ -420,6 +461,20 @@ struct b2sd_engine {
         d.epi.acc_scale = acc_scale; d.epi.res_scale = res_scale;
         d.epi.flags = flags;
         d.epi.n_valid = cout;
+        // the TAESD body at 256x256 and above: persistent halo-tile kernel with resident weights (tconv.cu)
+        static const bool no_tconv = getenv("B2_NO_TCONV") != nullptr;
+        static const char* tc_min = getenv("B2_TCONV_MIN_TILES");
+        const long tiles = (long)y.n * ((y.h + TC_TH - 1) / TC_TH) * ((y.w + TC_TW - 1) / TC_TW);
+        if (!no_tconv && stride == 1 && tconv_eligible(d) && tiles >= (tc_min ? atoi(tc_min) : 2 * 148)) {
+            TconvPlan tp;
+            TRY(tconv_plan(d, &tp));
+            char label[256];
+            snprintf(label, sizeof(label), "tconv %s rows=%ld tiles=%d grid=%u nbuf=%d", wkey.c_str(), tp.rows_total, tp.p.num_tiles,
+                     tp.grid.x, tp.p.nbuf);
+            if (&dst == &prog_frame) launches += 1;
+            dst.push_back(Op([tp](cudaStream_t st) { return tconv_launch(tp, st); }, label, 2.0 * (double)tp.rows_total * cout * K));
+            return 0;
+        }
         return add_igemm(dst, d);
     }
 
@@ -591,6 +646,7 @@ int b2sd_engine::build_transformer(const std::string& p, const Act& x, int heads
         d.epi.out = one_gemm ? vt : vt + (long)bi * HWp;
         d.epi.ldc = (int)vt_ld; d.epi.acc_scale = 1.f; d.epi.res_scale = 1.f;
         d.epi.n_valid = one_gemm ? (int)M : HW;
+        d.epi.flags = IG_CONST_A;   // the "activation view" is W_v; the `w` operand is the LayerNorm output of this frame
         TRY(add_igemm(prog_frame, d));
     }
     allow_swap = true;
@@ -632,6 +688,7 @@ int b2sd_engine::build_transformer(const std::string& p, const Act& x, int heads
         d.w = ctx; d.w_rows = L; d.w_ld = D; d.stride = 1;
         d.Nb = 1; d.Ho = 1; d.Wo = Cp;
         d.epi.out = vct; d.epi.ldc = Lpad; d.epi.acc_scale = 1.f; d.epi.res_scale = 1.f; d.epi.n_valid = L;
+        d.epi.flags = IG_CONST_A;
         TRY(add_igemm(prog_prompt, d));
         allow_swap = true;
     }
@@ -681,11 +738,10 @@ int b2sd_engine::build_transformer(const std::string& p, const Act& x, int heads
         d.BN = 128;
         d.epi.out = ff.p; d.epi.ldc = inner; d.epi.colbias = bff1; d.epi.acc_scale = 1.f; d.epi.res_scale = 1.f;
         d.epi.flags = IG_GEGLU; d.epi.n_valid = inner;
+        if (!getenv("B2_NO_EARLY")) d.epi.flags |= IG_CONST_B;
         IgemmPlan plan;
         TRY(igemm_plan(d, &plan));
-        ++launches;
-        prog_frame.push_back(Op([plan](cudaStream_t st) { return igemm_launch(plan, st); }, "igemm geglu " + p,
-                               2.0 * (double)M * (2.0 * inner) * C));
+        push_igemm(prog_frame, plan, d, "igemm geglu " + p, 2.0 * (double)M * (2.0 * inner) * C);
     }
     const Raw* wff2 = get(t + "ff.net.2.weight");
     if (!wff2) return -1;
@@ -887,6 +943,7 @@ int b2sd_engine::build_program(cudaStream_t s) {
     }
     taps["image"] = image;
     ++launches;  // post_u8 tail
+    link_weight_prefetch(prog_frame);
     CUDA_OK(cudaStreamSynchronize(s));
     built = true;
     return 0;
@@ -925,7 +982,7 @@ int b2sd_create(const b2sd_config* cfg, b2sd_handle* out) {
         b2_set_error("b2sd_create: device sm_%d%d is not Blackwell sm_100 (kernels are sm_100a only)", prop.major, prop.minor);
         return -1;
     }
-    if (igemm_init() || attn_init()) return -1;
+    if (igemm_init() || attn_init() || tconv_init()) return -1;
     b2sd_engine* e = new b2sd_engine();
     e->cfg = *cfg;
     e->lh = cfg->height / 8;
@@ -941,11 +998,9 @@ int b2sd_create(const b2sd_config* cfg, b2sd_handle* out) {
     e->temb_h = static_cast<float*>(e->state.alloc((size_t)B * 4 * C0 * sizeof(float)));
     e->temb = static_cast<float*>(e->state.alloc((size_t)B * 4 * C0 * sizeof(float)));
     e->gn_ws = static_cast<float*>(e->state.alloc(groupnorm_partial_floats(B, cfg->norm_groups) * sizeof(float)));
-    e->splitk_floats = (size_t)24 << 20;  // 96 MB of fp32 partials
-    e->splitk_ws = static_cast<float*>(e->state.alloc(e->splitk_floats * sizeof(float)));
     e->tile_counters = static_cast<int*>(e->state.alloc(65536 * sizeof(int)));
     if (e->tile_counters) cudaMemset(e->tile_counters, 0, 65536 * sizeof(int));
-    if (!e->x_in.p || !e->noise || !e->coef || !e->tsteps || !e->ctx || !e->temb || !e->splitk_ws || !e->gn_ws) {
+    if (!e->x_in.p || !e->noise || !e->coef || !e->tsteps || !e->ctx || !e->temb || !e->gn_ws) {
         b2_set_error("b2sd_create: cudaMalloc failed");
         delete e;
         return -1;
@@ -970,7 +1025,16 @@ int b2sd_load_tensor(b2sd_handle h, const char* key, const void* ptr, int dtype,
     Raw r;
     r.shape.assign(shape, shape + ndim);
     const long n = r.numel();
-    r.p = static_cast<__half*>(h->weights.alloc((size_t)n * 2));
+    auto old = h->raw.find(key);
+    if (old != h->raw.end()) {
+        // Reload of a parameter (e.g. a LoRA swap): everything derived from the old values is stale.  The packed / fp32
+        // caches are keyed by parameter name, so drop them all (they are rebuilt by the next b2sd_prepare); a same-shape
+        // reload overwrites the device copy in place instead of growing the bump arena.
+        h->packed.clear();
+        h->fvec.clear();
+        if (old->second.shape == r.shape) r.p = old->second.p;
+    }
+    if (!r.p) r.p = static_cast<__half*>(h->weights.alloc((size_t)n * 2));
     if (!r.p) {
         b2_set_error("b2sd_load_tensor: cudaMalloc failed for %s", key);
         return -1;
@@ -1000,7 +1064,6 @@ int b2sd_load_tensor(b2sd_handle h, const char* key, const void* ptr, int dtype,
     }
     h->raw[key] = std::move(r);
     h->built = false;
-    // packed caches may refer to a replaced tensor
     return 0;
 }
 
@@ -1102,9 +1165,13 @@ int b2sd_step_ex(b2sd_handle h, const void* frame_in, int in_kind, int in_h, int
             int rc = h->run(h->prog_frame, cs);
             cudaError_t ec = cudaStreamEndCapture(cs, &h->graph);
             cudaStreamDestroy(cs);
-            if (rc) return -1;
-            CUDA_OK(ec);
-            CUDA_OK(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
+            if (rc || ec != cudaSuccess || cudaGraphInstantiate(&h->graph_exec, h->graph, 0) != cudaSuccess) {
+                if (h->graph) cudaGraphDestroy(h->graph);   // a failed capture must not leave a half-built graph behind
+                h->graph = nullptr;
+                h->graph_exec = nullptr;
+                if (!rc) b2_set_error("b2sd_step: CUDA graph capture / instantiation failed: %s", cudaGetErrorString(ec != cudaSuccess ? ec : cudaGetLastError()));
+                return -1;
+            }
         }
         CUDA_OK(cudaGraphLaunch(h->graph_exec, s));
     } else {

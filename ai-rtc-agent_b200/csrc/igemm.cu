@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "epilogue.cuh"
 #include "launch.cuh"
 #include "ptx.cuh"
 
@@ -28,190 +29,6 @@ void b2_set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
-}
-
-// ------------------------------------------------------------------------------------------
-// epilogue math (shared by the main kernel and the split-K finalize kernel)
-__device__ __forceinline__ float gelu_erf(float x) {
-    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
-}
-
-__device__ __forceinline__ void store_half16(__half* dst, const float* v, int nv, bool vec_ok) {
-    if (nv == 16 && vec_ok) {
-        uint4 u[2];
-        __half2* h = reinterpret_cast<__half2*>(u);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-        reinterpret_cast<uint4*>(dst)[0] = u[0];
-        reinterpret_cast<uint4*>(dst)[1] = u[1];
-    } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-            if (i < nv) dst[i] = __float2half_rn(v[i]);
-    }
-}
-
-// 16 accumulator columns [col0, col0+16) of output row `orow` (batch item b); the accumulators are
-// acc[OFF .. OFF+16) of a register array (compile-time indices only: nothing may spill to local memory).
-template <int OFF, int N, typename T>
-__device__ __forceinline__ void epi_store16(const IgEpilogue& e, const T (&acc)[N], int b, long orow, int col0) {
-    int nv = e.n_valid - col0;
-    if (nv <= 0) return;
-    if (nv > 16) nv = 16;
-    float v[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        if constexpr (sizeof(T) == 4 && !__is_same(T, float)) v[i] = __uint_as_float(acc[OFF + i]);
-        else v[i] = acc[OFF + i];
-    }
-    if (e.colbias) {
-        const float* bp = e.colbias + (long)b * e.colbias_bstride + col0;
-        if (nv == 16 && (e.colbias_bstride & 3) == 0) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float4 t = reinterpret_cast<const float4*>(bp)[i];
-                v[4 * i + 0] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (i < nv) v[i] += bp[i];
-        }
-    }
-    if (e.acc_scale != 1.0f) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] *= e.acc_scale;
-    }
-    if (e.res) {
-        const __half* rp = e.res + orow * e.ldr + col0;
-        if (nv == 16 && (e.ldr & 7) == 0) {
-            uint4 u[2];
-            u[0] = reinterpret_cast<const uint4*>(rp)[0];
-            u[1] = reinterpret_cast<const uint4*>(rp)[1];
-            const __half2* h = reinterpret_cast<const __half2*>(u);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float2 f = __half22float2(h[i]);
-                v[2 * i] += e.res_scale * f.x;
-                v[2 * i + 1] += e.res_scale * f.y;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (i < nv) v[i] += e.res_scale * __half2float(rp[i]);
-        }
-    }
-    if (e.flags & IG_RELU) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
-    }
-    store_half16(e.out + orow * e.ldc + col0, v, nv, (e.ldc & 7) == 0);
-}
-
-// GEGLU: val/gate are 16 accumulator columns each; packed-column index of val[0] is pcol0 (bias
-// uses packed indexing), output column index is ocol0.
-__device__ __forceinline__ void epi_store16_geglu(const IgEpilogue& e, const uint32_t (&val)[16],
-                                                  const uint32_t (&gate)[16], long orow, int pcol_val,
-                                                  int pcol_gate, int ocol0) {
-    float v[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        float a = __uint_as_float(val[i]), g = __uint_as_float(gate[i]);
-        if (e.colbias) {
-            a += e.colbias[pcol_val + i];
-            g += e.colbias[pcol_gate + i];
-        }
-        v[i] = a * gelu_erf(g);
-    }
-    store_half16(e.out + orow * e.ldc + ocol0, v, 16, (e.ldc & 7) == 0);
-}
-
-// Fast epilogue of one output row (no split-K / GEGLU; n_valid % 16 == 0, vectorisable pitches): the residual row
-// is prefetched 32 columns ahead -- the first chunk even before the accumulator is ready -- so its global-memory
-// latency hides behind the mainloop instead of being paid once per 16-column chunk.
-__device__ __forceinline__ void epi_row_fast(const IgEpilogue& e, uint32_t taddr, int ncols, int gcol0, int b, long orow,
-                                             bool row_ok, uint64_t* wait_bar, uint32_t wait_parity = 0) {
-    const bool has_res = e.res != nullptr && row_ok;
-    const __half* rp = e.res ? e.res + orow * e.ldr + gcol0 : nullptr;
-    const float* bp = e.colbias ? e.colbias + (long)b * e.colbias_bstride + gcol0 : nullptr;
-    __half* op = e.out + orow * e.ldc + gcol0;
-    uint4 rr[4];
-    float4 bb[8];
-    auto fetch = [&](int c, uint4 (&r4)[4], float4 (&b8)[8]) {   // residual + bias of columns [c, c+32)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) r4[i] = make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) b8[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c >= ncols) return;
-        if (has_res) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (c + 8 * i < ncols) r4[i] = reinterpret_cast<const uint4*>(rp + c)[i];
-        }
-        if (bp) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (c + 4 * i < ncols) b8[i] = reinterpret_cast<const float4*>(bp + c)[i];
-        }
-    };
-    fetch(0, rr, bb);
-    if (wait_bar) {
-        mbar_wait(wait_bar, wait_parity);
-        tc_fence_after();
-    }
-    for (int c = 0; c < ncols; c += 32) {
-        const int left = ncols - c;   // >= 16, multiple of 16
-        uint32_t v[32];
-        if (left >= 32) {
-            tmem_ld32(taddr + c, v);
-        } else {
-            uint32_t lo[16];
-            tmem_ld16(taddr + c, lo);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { v[i] = lo[i]; v[16 + i] = 0; }
-        }
-        uint4 rn[4];
-        float4 bn[8];
-        fetch(c + 32, rn, bn);   // next pass: latency hides behind this pass
-        tmem_ld_wait();
-        if (row_ok) {
-            const float* bias = reinterpret_cast<const float*>(bb);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {   // 8 columns per 16-byte store
-                if (8 * g < left) {
-                    const __half2* rh = reinterpret_cast<const __half2*>(&rr[g]);
-                    uint4 o;
-                    __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int i = 8 * g + 2 * j;
-                        float x0 = (__uint_as_float(v[i]) + bias[i]) * e.acc_scale;
-                        float x1 = (__uint_as_float(v[i + 1]) + bias[i + 1]) * e.acc_scale;
-                        if (e.res) {
-                            const float2 f = __half22float2(rh[j]);
-                            x0 += e.res_scale * f.x;
-                            x1 += e.res_scale * f.y;
-                        }
-                        if (e.flags & IG_RELU) {
-                            x0 = fmaxf(x0, 0.f);
-                            x1 = fmaxf(x1, 0.f);
-                        }
-                        oh[j] = __floats2half2_rn(x0, x1);
-                    }
-                    reinterpret_cast<uint4*>(op + c)[g] = o;
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) rr[i] = rn[i];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) bb[i] = bn[i];
-    }
-}
-
-__device__ __forceinline__ bool epi_fast_ok(const IgEpilogue& e) {
-    return !(e.flags & (IG_SPLITK | IG_GEGLU)) && (e.n_valid & 15) == 0 && (e.ldc & 7) == 0 && (!e.res || (e.ldr & 7) == 0) &&
-           (e.colbias_bstride & 3) == 0;
 }
 
 // Swapped orientation: an accumulator row (TMEM lane, thread) is an output CHANNEL, its columns are the pixels of the
@@ -323,7 +140,7 @@ __device__ __forceinline__ void splitk_sum16(uint32_t stg_local, int cc, int row
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant__ IgemmParams p) {
+__global__ void __launch_bounds__(IG_THREADS, IG_THREADS <= 192 ? 2 : 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~static_cast<uintptr_t>(1023));
@@ -354,7 +171,7 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full_bar[s], 1);
-            mbar_init(&tmem_empty_bar[s], 128);
+            mbar_init(&tmem_empty_bar[s], IG_EPI_THREADS);
         }
         fence_mbar_init();
     }
@@ -366,6 +183,63 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+
+    // ---- TMA producer helpers (used by warp 0 / lane 0 only).  The k-block cursor walks (segment, tap, channel block).
+    struct KCursor { int seg, tap, cb; };
+    auto cursor_at = [&](int kb0) {
+        KCursor c{0, 0, 0};
+        int base = 0;
+        while (c.seg < p.nseg - 1 && kb0 >= base + p.seg_ntap[c.seg] * p.seg_cblocks[c.seg]) {
+            base += p.seg_ntap[c.seg] * p.seg_cblocks[c.seg];
+            ++c.seg;
+        }
+        c.tap = (kb0 - base) / p.seg_cblocks[c.seg];
+        c.cb = (kb0 - base) % p.seg_cblocks[c.seg];
+        return c;
+    };
+    auto cursor_next = [&](KCursor& c) {
+        if (++c.cb == p.seg_cblocks[c.seg]) {
+            c.cb = 0;
+            if (++c.tap == p.seg_ntap[c.seg]) {
+                c.tap = 0;
+                ++c.seg;
+            }
+        }
+    };
+    // normal: pixels -> A region (M side), weights -> B region.  swapped: weights (128 output channels) -> A region, pixels -> B
+    auto load_src = [&](int stage, const KCursor& c, int mt) {   // the 4-D "activation view" operand (tmA)
+        const int w0 = (mt % p.tiles_w) * p.tw, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
+        const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
+        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+        int dy = 0, dx = 0;
+        if (p.seg_ntap[c.seg] == 9) {
+            dy = c.tap / 3 - 1;
+            dx = c.tap % 3 - 1;
+        }
+        tma_load_4d(p.swap ? sa + IG_BM * IG_BK * 2 : sa, &p.tmA[c.seg], &full_bar[stage], p.seg_c0[c.seg] + c.cb * IG_BK,
+                    w0 * p.stride + dx, h0 * p.stride + dy, n0);
+    };
+    auto load_w = [&](int stage, int kb) {                        // the 2-D "weight matrix" operand (tmB)
+        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+        tma_load_2d(p.swap ? sa : sa + IG_BM * IG_BK * 2, &p.tmB, &full_bar[stage], kb * IG_BK, ntile * (p.swap ? IG_BM : p.BN));
+    };
+    // Operands that no earlier kernel of the stream writes (packed weights) do not have to wait for the programmatic
+    // dependency: the first ring pass of weight tiles is requested BEFORE griddepcontrol.wait, so its HBM latency overlaps the
+    // tail of the previous kernel, and the weights of the NEXT contraction of the frame are pulled into L2 (p.pf_*).
+    int early = 0;
+    if (warp == 0) {
+        if (p.pf_bytes) l2_prefetch_slice(p.pf_ptr, p.pf_bytes, lane);
+        if (lane == 0 && (p.epi.flags & (IG_CONST_B | IG_CONST_A)) && (int)blockIdx.x < num_mtiles && p.dbg_mode == 0) {
+            early = min(p.num_stages, kb_end - kb_begin);
+            KCursor c = cursor_at(kb_begin);
+            for (int s = 0; s < early; ++s) {
+                mbar_expect_tx(&full_bar[s], p.a_bytes + p.b_bytes);
+                if (p.epi.flags & IG_CONST_B) load_w(s, kb_begin + s);
+                if (p.epi.flags & IG_CONST_A) load_src(s, c, blockIdx.x);
+                cursor_next(c);
+            }
+        }
+    }
     pdl_launch_dependents();   // the next kernel may start its own prologue now
     pdl_wait();                // ... and everything below reads the previous kernel's output
     B2_TS(if (ts && threadIdx.x == 0) ts[1] = globaltimer_ns();)
@@ -377,42 +251,22 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             for (int mt = blockIdx.x; mt < num_mtiles; mt += gridDim.x) {
-                const int w0 = (mt % p.tiles_w) * p.tw, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
-                const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
-                int seg = 0, base = 0;
-                while (seg < p.nseg - 1 && kb_begin >= base + p.seg_ntap[seg] * p.seg_cblocks[seg]) {
-                    base += p.seg_ntap[seg] * p.seg_cblocks[seg];
-                    ++seg;
-                }
-                int tap = (kb_begin - base) / p.seg_cblocks[seg];
-                int cb = (kb_begin - base) % p.seg_cblocks[seg];
+                KCursor c = cursor_at(kb_begin);
                 for (int kb = kb_begin; kb < kb_end; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+#ifdef B2_BOUND_STUDY
                     if (p.dbg_mode == 1 && kb >= kb_begin + p.num_stages) {   // bound study: operands stay whatever they were
                         mbar_arrive(&full_bar[stage]);
                         if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
                         continue;
                     }
-                    mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
-                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                    uint8_t* sb = sa + IG_BM * IG_BK * 2;
-                    int dy = 0, dx = 0;
-                    if (p.seg_ntap[seg] == 9) {
-                        dy = tap / 3 - 1;
-                        dx = tap % 3 - 1;
-                    }
-                    // normal: pixels -> A (M side), weights -> B.  swapped: weights (128 output channels) -> A, pixels -> B
-                    tma_load_4d(p.swap ? sb : sa, &p.tmA[seg], &full_bar[stage], p.seg_c0[seg] + cb * IG_BK,
-                                w0 * p.stride + dx, h0 * p.stride + dy, n0);
-                    tma_load_2d(p.swap ? sa : sb, &p.tmB, &full_bar[stage], kb * IG_BK, ntile * (p.swap ? IG_BM : p.BN));
+#endif
+                    const bool armed = early > 0 && mt == (int)blockIdx.x && kb - kb_begin < early;   // requested before the PDL wait
+                    if (!armed) mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
+                    if (!(armed && (p.epi.flags & IG_CONST_A))) load_src(stage, c, mt);
+                    if (!(armed && (p.epi.flags & IG_CONST_B))) load_w(stage, kb);
                     B2_TS(if (ts && mt == (int)blockIdx.x && kb == kb_begin) ts[2] = globaltimer_ns();)
-                    if (++cb == p.seg_cblocks[seg]) {
-                        cb = 0;
-                        if (++tap == p.seg_ntap[seg]) {
-                            tap = 0;
-                            ++seg;
-                        }
-                    }
+                    cursor_next(c);
                     if (++stage == p.num_stages) {
                         stage = 0;
                         phase ^= 1;
@@ -443,9 +297,12 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                 const uint64_t da = make_kmajor_sw128_desc(sa);
                 const uint64_t db = make_kmajor_sw128_desc(sa + IG_BM * IG_BK * 2);
                 const uint32_t acc0 = kb > kb_begin ? 1u : 0u;
+#ifdef B2_BOUND_STUDY
                 if (p.dbg_mode == 2) {
                     if (elect_one()) umma_commit(&empty_bar[stage]);
-                } else if (elect_one()) {
+                } else
+#endif
+                if (elect_one()) {
                     // +32 B per UMMA_K inside the 128 B swizzle row => +2 in the (addr>>4) field
                     umma_f16(tacc, da, db, idesc, acc0);
                     umma_f16(tacc, da + 2, db + 2, idesc, 1u);
@@ -465,7 +322,11 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
         }
     } else {
         // ===== epilogue: TMEM -> registers -> global =====
+        // Optional second set of four epilogue warps (-DIG_THREADS=320: warps 6-9 see the same four TMEM lane quarters as 2-5
+        // and take the other half of a tile's columns).  Default build: one set -- 320 threads x 168 registers would leave
+        // one CTA per SM, and the co-residency of two CTAs (PDL overlap, persistent launches) is worth more.
         const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int eset = (IG_ESETS == 2 && warp >= 6) ? 1 : 0;
         const int r = q * 32 + lane;
         const int wi = r % p.tw;
         const int hi = (r / p.tw) % p.th;
@@ -486,7 +347,7 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                 tc_fence_after();
                 if (e.flags & IG_SPLITK) {
                     float4* stg = reinterpret_cast<float4*>(smem);
-                    for (int c = 0; c < p.BN; c += 16) {
+                    for (int c = eset * 16; c < p.BN; c += 16 * IG_ESETS) {
                         uint32_t v[16];
                         tmem_ld16(taddr + c, v);
                         tmem_ld_wait();
@@ -495,7 +356,7 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                             stg[((c >> 2) + i) * IG_BM + r] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
                                                                           __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
                     }
-                } else {
+                } else if (eset == 0) {
                     // the operand ring is idle (every MMA has retired): use its head as the transposition tile
                     float* T = reinterpret_cast<float*>(smem);
                     for (int c = 0; c < p.BN; c += SWAP_CH) {
@@ -514,7 +375,10 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
             } else if (epi_fast_ok(e)) {
                 int ncols = e.n_valid - ntile * p.BN;
                 if (ncols > p.BN) ncols = p.BN;
-                epi_row_fast(e, taddr, ncols, ntile * p.BN, n, orow, row_ok && ncols > 0, &tmem_full_bar[buf], par);
+                if (ncols < 0) ncols = 0;
+                const int csplit = IG_ESETS == 2 ? min(ncols, ((ncols >> 1) + 31) & ~31) : ncols;   // set 0: [0, csplit), set 1: [csplit, ncols)
+                const int c0 = eset ? csplit : 0, cn = eset ? ncols - csplit : csplit;
+                epi_row_fast(e, taddr + c0, cn, ntile * p.BN + c0, n, orow, row_ok && cn > 0, &tmem_full_bar[buf], par);
             } else {
                 mbar_wait(&tmem_full_bar[buf], par);
                 tc_fence_after();
@@ -524,7 +388,7 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                     // these stores and the peers' DSMEM reads are conflict-free; the reduction happens after the cluster
                     // barrier below.
                     float4* stg = reinterpret_cast<float4*>(smem);
-                    for (int c = 0; c < p.BN; c += 16) {
+                    for (int c = eset * 16; c < p.BN; c += 16 * IG_ESETS) {
                         uint32_t v[16];
                         tmem_ld16(taddr + c, v);
                         tmem_ld_wait();
@@ -535,7 +399,7 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                     }
                 } else if (e.flags & IG_GEGLU) {
                     const int half_n = p.BN / 2;
-                    for (int c = 0; c < half_n; c += 16) {
+                    for (int c = eset * 16; c < half_n; c += 16 * IG_ESETS) {
                         uint32_t a[16], g[16];
                         tmem_ld16(taddr + c, a);
                         tmem_ld16(taddr + half_n + c, g);
@@ -544,8 +408,7 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                             epi_store16_geglu(e, a, g, orow, ntile * p.BN + c, ntile * p.BN + half_n + c, ntile * half_n + c);
                     }
                 } else {
-                    int c = 0;
-                    for (; c + 32 <= p.BN; c += 32) {
+                    for (int c = eset * 32; c + 32 <= p.BN; c += 32 * IG_ESETS) {
                         uint32_t v[32];
                         tmem_ld32(taddr + c, v);
                         tmem_ld_wait();
@@ -554,7 +417,8 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                             epi_store16<16>(e, v, n, orow, ntile * p.BN + c + 16);
                         }
                     }
-                    if (c < p.BN) {
+                    if ((p.BN & 31) && eset == 0) {   // 16-column tail
+                        const int c = p.BN & ~31;
                         uint32_t v[16];
                         tmem_ld16(taddr + c, v);
                         tmem_ld_wait();
@@ -579,6 +443,7 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
         cluster_sync_all();  // all partial tiles are in place (release/acquire over the cluster)
         B2_TS(if (ts && threadIdx.x == 64) ts[6] = globaltimer_ns();)   // split launches: [5] staged, [6] cluster barrier passed, [7] reduced
         if (warp >= 2 && p.swap) {
+          if (warp < 6) {   // the transposition tile is swept by 128 threads (named barrier 1)
             // swapped orientation: this CTA finalises the pixel columns [rank*cols_per, (rank+1)*cols_per) of the tile
             const int rank = (int)cluster_ctarank();
             const int cols_per = p.BN / splits;
@@ -622,13 +487,14 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                 swap_store_chunk(p, pre, T, ntile, t);
                 epi_bar_sync();
             }
+          }
         } else if (warp >= 2) {
             const int rank = (int)cluster_ctarank();
             const int rows_per = IG_BM / splits;          // splits in {2,4,8}
-            const int t = threadIdx.x - 64;               // 0..127
+            const int t = threadIdx.x - 64;               // 0..255
             const int chunks = p.BN >> 4;
             const uint32_t stg_local = smem_u32(smem);
-            for (int item = t; item < rows_per * chunks; item += 128) {
+            for (int item = t; item < rows_per * chunks; item += IG_EPI_THREADS) {
                 const int rl = item % rows_per;
                 const int cc = item / rows_per;
                 const int r = rank * rows_per + rl;       // row of the tile this CTA finalises
@@ -651,275 +517,6 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
     B2_TS(if (ts && threadIdx.x == 32 && !(p.epi.flags & IG_SPLITK)) ts[7] = globaltimer_ns();)
-}
-
-// ------------------------------------------------------------------------------------------
-// halo-reuse 3x3 convolution kernel (see Conv3Params)
-__global__ void __launch_bounds__(C3_THREADS) conv3_kernel(const __grid_constant__ Conv3Params p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                               ~static_cast<uintptr_t>(1023));
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    uint8_t* sA = smem;                                   // 2 halo buffers
-    uint8_t* sB = smem + 2 * (size_t)p.abuf_bytes;        // weight-tile ring
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + (size_t)p.num_bstages * p.b_bytes);
-    uint64_t* a_empty = a_full + 2;
-    uint64_t* b_full = a_empty + 2;
-    uint64_t* b_empty = b_full + C3_MAX_BSTAGES;
-    uint64_t* tmem_full_bar = b_empty + C3_MAX_BSTAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-
-    const int TW = 8 * p.MT;
-    const int bx = blockIdx.x;
-    const int tiw = bx % p.tiles_w;
-    const int tih = (bx / p.tiles_w) % p.tiles_h;
-    const int n0 = bx / (p.tiles_w * p.tiles_h);
-    const int w0 = tiw * TW, h0 = tih * C3_TH;
-    const int ntile = blockIdx.y;
-    const int u_begin = blockIdx.z * p.units_per_split;
-    const int u_end = min(p.units_total, u_begin + p.units_per_split);
-    [[maybe_unused]] unsigned long long* ts = p.dbg_ts ? p.dbg_ts + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
-    B2_TS(if (ts && threadIdx.x == 0) ts[0] = globaltimer_ns();)
-
-    if (warp == 0 && lane == 0) {
-        for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.tmA[s]);
-        tma_prefetch_desc(&p.tmB);
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&a_full[s], 1);
-            mbar_init(&a_empty[s], 1);
-        }
-        for (int s = 0; s < p.num_bstages; ++s) {
-            mbar_init(&b_full[s], 1);
-            mbar_init(&b_empty[s], 1);
-        }
-        mbar_init(tmem_full_bar, 1);
-        fence_mbar_init();
-    }
-    if (warp == 1) {
-        tmem_alloc(tmem_slot, p.tmem_cols);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    pdl_launch_dependents();   // the next kernel may start its own prologue now
-    pdl_wait();                // ... and everything below reads the previous kernel's output
-    B2_TS(if (ts && threadIdx.x == 0) ts[1] = globaltimer_ns();)
-
-    // unit -> (segment, channel block)
-    auto locate = [&](int u, int& seg, int& cb) {
-        seg = 0;
-        while (seg < p.nseg - 1 && u >= p.seg_cblocks[seg]) {
-            u -= p.seg_cblocks[seg];
-            ++seg;
-        }
-        cb = u;
-    };
-
-    if (warp == 6) {
-        if (lane == 0) {
-            // ===== A producer: one (halo) tile per unit =====
-            int seg, cb;
-            locate(u_begin, seg, cb);
-            for (int u = u_begin; u < u_end; ++u) {
-                const int slot = (u - u_begin) & 1;
-                mbar_wait(&a_empty[slot], (((u - u_begin) >> 1) & 1) ^ 1);
-                mbar_expect_tx(&a_full[slot], p.seg_abytes[seg]);
-                const int halo = p.seg_ntap[seg] == 9 ? 1 : 0;
-                tma_load_4d(sA + (size_t)slot * p.abuf_bytes, &p.tmA[seg], &a_full[slot], cb * IG_BK, w0 - halo, h0 - halo, n0);
-                B2_TS(if (ts && u == u_begin) ts[2] = globaltimer_ns();)
-                if (++cb == p.seg_cblocks[seg]) {
-                    cb = 0;
-                    ++seg;
-                }
-            }
-        }
-    } else if (warp == 0) {
-        if (lane == 0) {
-            // ===== B producer: one weight tile [BN x 64] per (unit, tap) =====
-            int seg, cb;
-            locate(u_begin, seg, cb);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int u = u_begin; u < u_end; ++u) {
-                const int ntap = p.seg_ntap[seg];
-                for (int tap = 0; tap < ntap; ++tap) {
-                    mbar_wait(&b_empty[stage], phase ^ 1);
-                    mbar_expect_tx(&b_full[stage], p.b_bytes);
-                    tma_load_2d(sB + (size_t)stage * p.b_bytes, &p.tmB, &b_full[stage],
-                                p.seg_koff[seg] + tap * p.seg_c[seg] + cb * IG_BK, ntile * p.BN);
-                    if (++stage == p.num_bstages) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                }
-                if (++cb == p.seg_cblocks[seg]) {
-                    cb = 0;
-                    ++seg;
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer (whole warp, one elected lane issues; see igemm_kernel) =====
-        const uint32_t idesc = make_idesc_f16(IG_BM, p.BN);
-        int seg, cb;
-        locate(u_begin, seg, cb);
-        int stage = 0;
-        uint32_t phase = 0;
-        uint32_t acc = 0;
-        const uint32_t sa_base = smem_u32(sA), sb_base = smem_u32(sB);
-        for (int u = u_begin; u < u_end; ++u) {
-            const int slot = (u - u_begin) & 1;
-            mbar_wait(&a_full[slot], ((u - u_begin) >> 1) & 1);
-            B2_TS(if (ts && u == u_begin && lane == 0) ts[3] = globaltimer_ns();)
-            const int ntap = p.seg_ntap[seg];
-            const int pitch = ntap == 9 ? TW + 2 : TW;   // pixels per halo row
-            // descriptor of M-tile 0 at tap (0,0); rows of M-tile t: pixel (hi, 8t + wi) -> halo pixel hi*pitch + 8t + wi
-            // (+ tap shift).  8-row core groups are `pitch` pixels apart; the swizzle follows absolute address bits, so an
-            // unaligned start needs no base offset (probe.cu)
-            uint64_t da0 = 0;
-            da0 |= (uint64_t)(((sa_base + (uint32_t)slot * p.abuf_bytes) & 0x3ffff) >> 4);
-            da0 |= (uint64_t)1 << 16;
-            da0 |= (uint64_t)((pitch * 128) >> 4) << 32;
-            da0 |= (uint64_t)1 << 46;
-            da0 |= (uint64_t)2 << 61;
-            for (int tap = 0; tap < ntap; ++tap) {
-                if (!(p.epi.flags & 128)) mbar_wait(&b_full[stage], phase);
-                tc_fence_after();
-                const uint64_t db = make_kmajor_sw128_desc(sb_base + (uint32_t)stage * p.b_bytes);
-                const int shift = ntap == 9 ? (tap / 3) * pitch + (tap % 3) : 0;   // pixels (128 B each => 8 in addr>>4 units)
-                const uint64_t da = da0 + (uint64_t)(shift * 8);
-                if (elect_one()) {
-                    umma_f16(tmem_base, da, db, idesc, acc);
-                    umma_f16(tmem_base, da + 2, db + 2, idesc, 1u);
-                    umma_f16(tmem_base, da + 4, db + 4, idesc, 1u);
-                    umma_f16(tmem_base, da + 6, db + 6, idesc, 1u);
-                    if (p.MT == 2) {
-                        const uint64_t da1 = da + 64;   // 8 pixels to the right
-                        const uint32_t t1 = tmem_base + (uint32_t)p.BN;
-                        umma_f16(t1, da1, db, idesc, acc);
-                        umma_f16(t1, da1 + 2, db + 2, idesc, 1u);
-                        umma_f16(t1, da1 + 4, db + 4, idesc, 1u);
-                        umma_f16(t1, da1 + 6, db + 6, idesc, 1u);
-                    }
-                    umma_commit(&b_empty[stage]);
-                }
-                __syncwarp();
-                acc = 1u;
-                if (++stage == p.num_bstages) {
-                    stage = 0;
-                    phase ^= 1;
-                }
-            }
-            if (elect_one()) umma_commit(&a_empty[slot]);
-            __syncwarp();
-            if (++cb == p.seg_cblocks[seg]) {
-                cb = 0;
-                ++seg;
-            }
-        }
-        if (elect_one()) umma_commit(tmem_full_bar);
-        __syncwarp();
-        B2_TS(if (ts && lane == 0) ts[4] = globaltimer_ns();)
-    } else {
-        // ===== epilogue =====
-        const int q = warp & 3;
-        const int r = q * 32 + lane;
-        const int hi = r >> 3, wl = r & 7;
-        const int h = h0 + hi;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        const IgEpilogue& e = p.epi;
-        if (epi_fast_ok(e)) {
-            int ncols = e.n_valid - ntile * p.BN;
-            if (ncols > p.BN) ncols = p.BN;
-            for (int t = 0; t < p.MT; ++t) {
-                const int w = w0 + 8 * t + wl;
-                const bool row_ok = (h < p.Ho) && (w < p.Wo) && ncols > 0;
-                epi_row_fast(e, taddr + t * p.BN, ncols, ntile * p.BN, n0, ((long)n0 * p.Ho + h) * p.Wo + w, row_ok,
-                             t == 0 ? tmem_full_bar : nullptr);
-            }
-            B2_TS(if (ts && threadIdx.x == 64) ts[5] = globaltimer_ns();)
-        } else {
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
-        B2_TS(if (ts && threadIdx.x == 64) ts[5] = globaltimer_ns();)
-        if (e.flags & IG_SPLITK) {
-            float4* stg = reinterpret_cast<float4*>(smem);
-            for (int t = 0; t < p.MT; ++t)
-                for (int c = 0; c < p.BN; c += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(taddr + t * p.BN + c, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        stg[(t * (p.BN >> 2) + (c >> 2) + i) * IG_BM + r] =
-                            make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                                        __uint_as_float(v[4 * i + 3]));
-                }
-        } else {
-            for (int t = 0; t < p.MT; ++t) {
-                const int w = w0 + 8 * t + wl;
-                const bool row_ok = (h < p.Ho) && (w < p.Wo);
-                const long orow = ((long)n0 * p.Ho + h) * p.Wo + w;
-                int c = 0;
-                for (; c + 32 <= p.BN; c += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + t * p.BN + c, v);
-                    tmem_ld_wait();
-                    if (row_ok) {
-                        epi_store16<0>(e, v, n0, orow, ntile * p.BN + c);
-                        epi_store16<16>(e, v, n0, orow, ntile * p.BN + c + 16);
-                    }
-                }
-                if (c < p.BN) {
-                    uint32_t v[16];
-                    tmem_ld16(taddr + t * p.BN + c, v);
-                    tmem_ld_wait();
-                    if (row_ok) epi_store16<0>(e, v, n0, orow, ntile * p.BN + c);
-                }
-            }
-        }
-        }  // generic (non-prefetching) epilogue
-    }
-    B2_TS(if (ts && threadIdx.x == 64) ts[6] = globaltimer_ns();)
-    if (p.epi.flags & IG_SPLITK) {
-        const int splits = (int)gridDim.z;
-        cluster_sync_all();
-        if (warp >= 2 && warp < 6) {
-            const int rank = (int)cluster_ctarank();
-            const int rows_per = IG_BM / splits;
-            const int tt = threadIdx.x - 64;
-            const int chunks = p.BN >> 4;
-            const uint32_t stg_local = smem_u32(smem);
-            for (int item = tt; item < rows_per * chunks * p.MT; item += 128) {
-                const int rl = item % rows_per;
-                const int cc = (item / rows_per) % chunks;
-                const int t = item / (rows_per * chunks);
-                const int r = rank * rows_per + rl;
-                const int h = h0 + (r >> 3), w = w0 + 8 * t + (r & 7);
-                float acc[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-                for (int sidx = 0; sidx < splits; ++sidx) {
-                    const uint32_t peer = dsmem_map(stg_local, (uint32_t)sidx);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 v = dsmem_ld_f4(peer + (uint32_t)(((t * (p.BN >> 2) + cc * 4 + i) * IG_BM + r) * 16));
-                        acc[4 * i] += v.x; acc[4 * i + 1] += v.y; acc[4 * i + 2] += v.z; acc[4 * i + 3] += v.w;
-                    }
-                }
-                if (h < p.Ho && w < p.Wo)
-                    epi_store16<0>(p.epi, acc, n0, ((long)n0 * p.Ho + h) * p.Wo + w, ntile * p.BN + cc * 16);
-            }
-        }
-        cluster_sync_all();
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
-    B2_TS(if (ts && threadIdx.x == 32) ts[7] = globaltimer_ns();)
 }
 
 // ------------------------------------------------------------------------------------------
@@ -988,75 +585,6 @@ size_t igemm_partial_floats(int splits, long rows_total, int n_valid) {
     // worst case n_pad = n_tiles * BN < n_valid + 256
     long n_pad = ((n_valid + 255) / 256 + 1) * 256;
     return (size_t)splits * rows_total * n_pad;
-}
-
-// Upgrade a stride-1 3x3 plan to the halo-reuse kernel when eligible (otherwise leaves mode 0).
-static int plan_halo(const IgemmDesc& d, int BN, int n_tiles, int splits_req, IgemmPlan* plan) {
-    // opt-in for now: with 64-wide N tiles the halo kernel is MMA-issue bound and loses to the tap kernel
-    static const bool disabled = getenv("B2_HALO") == nullptr || getenv("B2_NO_HALO") != nullptr;
-    if (disabled || d.stride != 1 || (d.epi.flags & IG_GEGLU) || d.Wo < 8) return 0;
-    bool any9 = false;
-    for (int s = 0; s < d.nseg; ++s) {
-        any9 |= d.ntap[s] == 9;
-        if (d.src[s].H != d.Ho || d.src[s].W != d.Wo || d.src[s].N != d.Nb) return 0;
-    }
-    if (!any9) return 0;
-    Conv3Params& c = plan->c3;
-    memset(&c, 0, sizeof(c));
-    c.MT = d.Wo >= 16 ? 2 : 1;
-    if (getenv("B2_FORCE_MT1")) c.MT = 1;
-    const int TW = 8 * c.MT;
-    c.BN = BN;
-    c.tiles_w = (d.Wo + TW - 1) / TW;
-    c.tiles_h = (d.Ho + C3_TH - 1) / C3_TH;
-    c.Wo = d.Wo; c.Ho = d.Ho; c.Nb = d.Nb;
-    c.nseg = d.nseg;
-    int koff = 0, units = 0;
-    uint32_t amax = 0;
-    for (int s = 0; s < d.nseg; ++s) {
-        const int halo = d.ntap[s] == 9 ? 2 : 0;
-        c.seg_ntap[s] = d.ntap[s];
-        c.seg_cblocks[s] = d.src[s].C / IG_BK;
-        c.seg_c[s] = d.src[s].C;
-        c.seg_koff[s] = koff;
-        koff += d.ntap[s] * d.src[s].C;
-        units += c.seg_cblocks[s];
-        c.seg_abytes[s] = (uint32_t)(TW + halo) * (C3_TH + halo) * IG_BK * 2;
-        if (c.seg_abytes[s] > amax) amax = c.seg_abytes[s];
-        if (encode_act_map(&c.tmA[s], d.src[s], IG_BK, TW + halo, C3_TH + halo, 1, 1)) return -1;
-    }
-    if (encode_w_map(&c.tmB, d.w, d.w_rows, d.w_ld, BN)) return -1;
-    c.units_total = units;
-    c.abuf_bytes = (amax + 1023u) & ~1023u;
-    c.b_bytes = (uint32_t)BN * IG_BK * 2;
-    int splits = splits_req < 1 ? 1 : splits_req;
-    while (splits > units) splits >>= 1;
-    if (splits < 1) splits = 1;
-    c.units_per_split = (units + splits - 1) / splits;
-    while (splits > 1 && (units + c.units_per_split - 1) / c.units_per_split != splits) {
-        splits >>= 1;
-        c.units_per_split = (units + splits - 1) / splits;
-    }
-    const size_t budget = 200 * 1024;
-    int stages = (int)((budget - 2 * (size_t)c.abuf_bytes) / c.b_bytes);
-    if (stages > C3_MAX_BSTAGES) stages = C3_MAX_BSTAGES;
-    if (stages < 3) return 0;  // does not fit: stay on the tap-by-tap kernel
-    c.num_bstages = stages;
-    const size_t pipe = 2 * (size_t)c.abuf_bytes + (size_t)stages * c.b_bytes;
-    if (splits > 1 && (size_t)c.MT * BN * IG_BM * 4 > pipe) return 0;
-    uint32_t cols = 32;
-    while (cols < (uint32_t)(c.MT * BN)) cols <<= 1;
-    if (cols > 512) return 0;
-    c.tmem_cols = cols;
-    c.epi = d.epi;
-    c.dbg_ts = d.dbg_ts;
-    if (getenv("B2_DEBUG_NOWAITB")) c.epi.flags |= 128;
-    if (splits > 1) c.epi.flags |= IG_SPLITK;
-    plan->mode = 1;
-    plan->splits = splits;
-    plan->smem = pipe + 1024 + 512;
-    plan->grid = dim3(c.tiles_w * c.tiles_h * d.Nb, n_tiles, splits);
-    return 0;
 }
 
 // Swapped orientation plan: output channels on the M side (128 per CTA), a tile of BN pixels on the N side.
@@ -1326,8 +854,13 @@ int igemm_plan(const IgemmDesc& d, IgemmPlan* plan) {
     p.tmem_cols = cols;
     plan->grid = dim3(grid_x, n_tiles, splits);
     plan->mode = 0;
-    return plan_halo(d, BN, n_tiles, splits, plan);
+    return 0;
 }
+
+int igemm_encode_act_map(CUtensorMap* m, const ActView& a, int box_c, int box_w, int box_h, int box_n, int estride) {
+    return encode_act_map(m, a, box_c, box_w, box_h, box_n, estride);
+}
+int igemm_encode_w_map(CUtensorMap* m, const __half* w, int rows, int ld, int box_rows) { return encode_w_map(m, w, rows, ld, box_rows); }
 
 int igemm_init() {
     static bool attr_set = false;
@@ -1336,11 +869,6 @@ int igemm_init() {
                                              227 * 1024);
         if (e != cudaSuccess) {
             b2_set_error("cudaFuncSetAttribute(igemm): %s", cudaGetErrorString(e));
-            return -1;
-        }
-        e = cudaFuncSetAttribute(conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) {
-            b2_set_error("cudaFuncSetAttribute(conv3): %s", cudaGetErrorString(e));
             return -1;
         }
         if (!get_encode()) return -1;
@@ -1352,8 +880,7 @@ int igemm_init() {
 int igemm_launch(const IgemmPlan& plan, cudaStream_t stream) {
     if (igemm_init()) return -1;
     const int cz = plan.splits > 1 ? plan.splits : 1;
-    cudaError_t e = plan.mode == 1 ? launch_k(conv3_kernel, plan.grid, dim3(C3_THREADS), plan.smem, stream, cz, plan.c3)
-                                   : launch_k(igemm_kernel, plan.grid, dim3(IG_THREADS), plan.smem, stream, cz, plan.p);
+    cudaError_t e = launch_k(igemm_kernel, plan.grid, dim3(IG_THREADS), plan.smem, stream, cz, plan.p);
     if (e != cudaSuccess) {
         b2_set_error("igemm launch: %s", cudaGetErrorString(e));
         return -1;

@@ -18,12 +18,21 @@ constexpr int IG_BM = 128;        // rows (pixels/tokens) per CTA tile == UMMA M
 constexpr int IG_BK = 64;         // fp16 elements per K-block (128 B = one swizzle row)
 constexpr int IG_MAX_SRC = 3;
 constexpr int IG_MAX_STAGES = 8;
+#ifndef IG_THREADS_OVERRIDE
 constexpr int IG_THREADS = 192;   // warp0: TMA, warp1: MMA + TMEM alloc, warps 2-5: epilogue
+#else
+constexpr int IG_THREADS = IG_THREADS_OVERRIDE;   // 320: a second set of four epilogue warps (experiment)
+#endif
+constexpr int IG_EPI_THREADS = IG_THREADS - 64;
+constexpr int IG_ESETS = IG_EPI_THREADS / 128;
 
 enum : int {
     IG_RELU = 1,    // relu after bias/residual
     IG_GEGLU = 2,   // tile columns [0,BN/2) = value, [BN/2,BN) = gate; out = v * gelu_erf(g)
     IG_SPLITK = 4,  // set by the planner: K is split over a thread-block cluster, partial tiles are reduced through DSMEM
+    IG_CONST_B = 16,  // the weight-matrix operand (IgemmDesc::w) is never written by a kernel of the stream: it may be fetched
+                      // before the programmatic-dependency wait
+    IG_CONST_A = 32,  // same for the activation-view operand (src[]) -- the V^T GEMM, whose "activations" are the weights
 };
 
 struct IgEpilogue {
@@ -62,35 +71,9 @@ struct IgemmParams {
     int n_pad;
     int swap;                     // 1: weights on the M side (128 output channels per CTA), pixels on the N side
     int tw_log2, th_log2;         // swap mode: pixel-tile extents are powers of two
-    int dbg_mode;                 // bound study (env B2_DBG_MODE): 1 = TMA loads only for the first ring pass, 2 = no MMAs
-    IgEpilogue epi;
-};
-
-// ---- halo-reuse 3x3 convolution (stride 1): one TMA load of a (16+2) x (TW+2) pixel halo tile per 64-channel
-// block feeds all nine filter taps (shifted UMMA descriptors), and MT = 1 or 2 M-tiles of 128 pixels share every
-// weight tile.  Cuts L2->SM operand traffic ~4x versus nine independent tap loads per M-tile.
-constexpr int C3_THREADS = 224;   // warp0: B (weights) TMA, warp1: MMA, warps 2-5: epilogue, warp6: A (halo) TMA
-constexpr int C3_TH = 16;         // output rows per tile; tile width = 8 * MT
-constexpr int C3_MAX_BSTAGES = 8;
-struct Conv3Params {
-    CUtensorMap tmA[IG_MAX_SRC];
-    CUtensorMap tmB;
-    int seg_ntap[IG_MAX_SRC];
-    int seg_cblocks[IG_MAX_SRC];
-    int seg_koff[IG_MAX_SRC];     // K offset (elements) of the segment inside a packed weight row
-    int seg_c[IG_MAX_SRC];        // channels of the segment
-    uint32_t seg_abytes[IG_MAX_SRC];
-    int nseg;
-    int units_total;              // sum of cblocks: one unit = one halo tile + its taps
-    int units_per_split;
-    int MT, BN;
-    int tiles_w, tiles_h;
-    int Wo, Ho, Nb;
-    int num_bstages;
-    uint32_t abuf_bytes;          // one A buffer (1024-aligned)
-    uint32_t b_bytes;
-    uint32_t tmem_cols;
-    unsigned long long* dbg_ts;
+    int dbg_mode;                 // bound study (-DB2_BOUND_STUDY + env B2_DBG_MODE): 1 = TMA loads only for the first ring pass, 2 = no MMAs
+    const void* pf_ptr;           // weights of the NEXT contraction of the frame program: pulled into L2 while this one runs
+    unsigned long long pf_bytes;  // (0 = nothing to prefetch; multiple of 16)
     IgEpilogue epi;
 };
 
@@ -119,8 +102,7 @@ struct IgemmDesc {
 };
 
 struct IgemmPlan {
-    int mode;       // 0: igemm_kernel (tap-by-tap loads), 1: conv3_kernel (halo reuse)
-    Conv3Params c3;
+    int mode;       // always 0 (igemm_kernel); kept for the plan-info ABI
     IgemmParams p;
     dim3 grid;
     size_t smem;

@@ -67,6 +67,9 @@ IN_U8_NHWC, IN_F32_NCHW, IN_F16_NCHW = 0, 1, 2
 OUT_U8_NCHW, OUT_F16_NCHW = 0, 1
 IG_RELU = 1
 IG_GEGLU = 2
+IG_CONST_W = 16
+IG_CONST_SRC = 32
+IG_TCONV = 64
 
 _lib = None
 

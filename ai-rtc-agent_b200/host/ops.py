@@ -31,7 +31,8 @@ def _view(t: torch.Tensor) -> capi.ActView:
 def igemm(srcs: Sequence[Tuple[torch.Tensor, int]], w: torch.Tensor, out: torch.Tensor, *,
           stride: int = 1, colbias: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
           acc_scale: float = 1.0, res_scale: float = 1.0, relu: bool = False, geglu: bool = False,
-          bn: int = 0, splits: int = 1, n_valid: Optional[int] = None, timeline: Optional[torch.Tensor] = None, swap: bool = False) -> torch.Tensor:
+          bn: int = 0, splits: int = 1, n_valid: Optional[int] = None, timeline: Optional[torch.Tensor] = None, swap: bool = False,
+          const_w: bool = False, const_src: bool = False, tconv: bool = False) -> torch.Tensor:
     """srcs: [(NHWC fp16 tensor, ntap)], w: packed fp16 [rows, K]; out: NHWC fp16 [nb,ho,wo,ldc>=n]."""
     d = capi.IgemmDesc()
     d.nseg = len(srcs)
@@ -58,7 +59,8 @@ def igemm(srcs: Sequence[Tuple[torch.Tensor, int]], w: torch.Tensor, out: torch.
         assert res.dtype == torch.float16
         d.res, d.ldr = res.data_ptr(), res.stride(2)
     d.acc_scale, d.res_scale = acc_scale, res_scale
-    d.flags = (capi.IG_RELU if relu else 0) | (capi.IG_GEGLU if geglu else 0)
+    d.flags = ((capi.IG_RELU if relu else 0) | (capi.IG_GEGLU if geglu else 0) | (capi.IG_CONST_W if const_w else 0) |
+               (capi.IG_CONST_SRC if const_src else 0) | (capi.IG_TCONV if tconv else 0))
     capi.check(capi.lib().b2sd_op_igemm(C.byref(d), capi.current_stream_ptr()), "b2sd_op_igemm")
     return out
 

@@ -101,25 +101,92 @@ class StreamDiffusionPipeline:
         return frame.mul(255.0).clamp_(0, 255).to(torch.uint8)[None]
 
     def __call__(self, frame):
+        """lib/pipeline.py:76-96, blocking semantics preserved: the result is complete when the call returns only in the
+        software-encode branch (`.cpu()`); with NVENC set the CUDA tensor is returned stream-ordered, like the reference."""
+        return self.enqueue(frame).result(wait=not os.getenv("NVENC"))
+
+    # ---- non-blocking entry (SURVEY.md 8f-2): everything is queued on CUDA streams and a ticket comes back at once ------
+    def enqueue(self, frame) -> "FrameTicket":
+        """Queue one frame and return immediately.  GPU frames (NVDEC path) go straight to the engine on the current
+        stream.  av.VideoFrame input is staged through a pinned ring and copied on a separate copy stream, so the upload of
+        frame n+1 overlaps the compute of frame n; with NVENC unset the download of the result is queued the same way.
+        Tickets complete in submission order (one temporal stream per pipeline, like the reference)."""
         if not _is_gpu_frame(frame) and not _is_video_frame(frame):
             raise Exception("invalid frame type")
+        dev = self.model.stream.device
+        compute = torch.cuda.current_stream(dev)
         if _is_video_frame(frame):
-            rgb = torch.from_numpy(frame.to_ndarray(format="rgb24")).unsqueeze(0).to(self.device)
+            self._ensure_staging(dev)
+            slot = self._slot
+            self._slot = (slot + 1) % len(self._pinned_in)
+            self._slot_free[slot].synchronize()          # the ring entry's previous upload has been consumed (depth-4 ring)
+            arr = frame.to_ndarray(format="rgb24")
+            host = self._pinned_in[slot]
+            if tuple(arr.shape) != tuple(host.shape[1:]):
+                host = self._pinned_in[slot] = torch.empty((1,) + tuple(arr.shape), dtype=torch.uint8).pin_memory()
+            host[0].copy_(torch.from_numpy(arr))
+            with torch.cuda.stream(self._copy_stream):
+                rgb = host.to(dev, non_blocking=True)
+                uploaded = torch.cuda.Event()
+                uploaded.record(self._copy_stream)
+            compute.wait_event(uploaded)
+            rgb.record_stream(compute)
         else:
+            slot = None
             rgb = _as_torch_u8_nhwc(frame, self.device)
         post_output = self.model.stream.step_u8(rgb)
+        if slot is not None:
+            self._slot_free[slot].record(compute)
+        done = torch.cuda.Event()
+        if os.getenv("NVENC"):
+            done.record(compute)
+            return FrameTicket(post_output, done, None, None)
+        # software-encode branch (lib/pipeline.py:83-94): hand back an av.VideoFrame with the input's timing
+        assert _is_video_frame(frame)
+        self._ensure_staging(dev)
+        host_out = torch.empty((1, 3, self.model.height, self.model.width), dtype=torch.uint8).pin_memory()
+        computed = torch.cuda.Event()
+        computed.record(compute)
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(computed)
+            host_out.copy_(post_output, non_blocking=True)
+            post_output.record_stream(self._copy_stream)
+            done.record(self._copy_stream)
+        return FrameTicket(post_output, done, host_out, frame)
 
-        if not os.getenv("NVENC"):
-            # software-encode branch (lib/pipeline.py:83-94): hand back an av.VideoFrame with the input's timing
-            try:
-                import av
-            except ImportError as exc:
-                raise RuntimeError("NVENC is unset, so an av.VideoFrame must be returned, but PyAV is not installed; "
-                                   "set NVENC=1 to receive the CUDA tensor") from exc
-            assert _is_video_frame(frame)
-            hwc = post_output.cpu().permute(0, 2, 3, 1).squeeze(0).numpy()
-            out = av.VideoFrame.from_ndarray(np.ascontiguousarray(hwc))
-            out.pts = frame.pts
-            out.time_base = frame.time_base
-            return out
-        return post_output
+    def _ensure_staging(self, dev) -> None:
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._pinned_in = [torch.empty((1, self.model.height, self.model.width, 3), dtype=torch.uint8).pin_memory()
+                               for _ in range(4)]
+            self._slot_free = [torch.cuda.Event() for _ in range(4)]
+            self._slot = 0
+
+
+class FrameTicket:
+    """Result handle of StreamDiffusionPipeline.enqueue()."""
+
+    def __init__(self, tensor: torch.Tensor, done: "torch.cuda.Event", host_out: Optional[torch.Tensor], src_frame):
+        self._tensor, self._done, self._host_out, self._src = tensor, done, host_out, src_frame
+
+    def done(self) -> bool:
+        """True once every GPU operation of this frame (and the download, if any) has finished; never blocks."""
+        return self._done.query()
+
+    def result(self, wait: bool = True):
+        """The (1,3,H,W) u8 CUDA tensor (NVENC set) or an av.VideoFrame carrying the input's pts/time_base."""
+        if self._host_out is None:
+            if wait:
+                self._done.synchronize()
+            return self._tensor
+        try:
+            import av
+        except ImportError as exc:
+            raise RuntimeError("NVENC is unset, so an av.VideoFrame must be returned, but PyAV is not installed; "
+                               "set NVENC=1 to receive the CUDA tensor") from exc
+        self._done.synchronize()
+        hwc = self._host_out.permute(0, 2, 3, 1).squeeze(0).numpy()
+        out = av.VideoFrame.from_ndarray(np.ascontiguousarray(hwc))
+        out.pts = self._src.pts
+        out.time_base = self._src.time_base
+        return out

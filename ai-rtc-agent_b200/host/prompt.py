@@ -43,10 +43,16 @@ class ClipPromptEncoder:
         return self.model(ids)[0].to(torch.float16)
 
 
-def make_prompt_encoder(model_dir: Optional[str], dim: int, device: str = "cuda"):
+def make_prompt_encoder(model_dir: Optional[str], dim: int, device: str = "cuda", allow_synthetic: bool = False):
+    """A checkpoint directory with a text_encoder/ must load (a real model fed hash-seeded embeddings renders garbage for
+    every prompt: failing is the only safe behaviour).  The synthetic encoder is for synthetic weights only."""
     if model_dir and os.path.isdir(os.path.join(model_dir, "text_encoder")):
-        try:
-            return ClipPromptEncoder(model_dir, device)
-        except Exception as exc:  # pragma: no cover - depends on local files
-            logger.warning("could not load the CLIP text encoder from %s (%s); using synthetic embeddings", model_dir, exc)
+        enc = ClipPromptEncoder(model_dir, device)
+        got = enc.model.config.hidden_size
+        if got != dim:
+            raise ValueError(f"text encoder under {model_dir} has hidden size {got}, the UNet cross-attention expects {dim}")
+        return enc
+    if model_dir and not allow_synthetic:
+        raise FileNotFoundError(f"{model_dir} has no text_encoder/: cannot encode prompts for a real checkpoint "
+                                f"(set B200SD_SYNTHETIC_WEIGHTS=1 to run with synthetic embeddings)")
     return SyntheticPromptEncoder(dim)

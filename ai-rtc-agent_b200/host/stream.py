@@ -96,6 +96,7 @@ class StreamDiffusion:
         self.similar_image_filter = False
         self.prev_image_result = None
         self.inference_time_ema = 0.0
+        self._ev = None
         self.image_processor = ImageProcessor(8)
         self.prompt_encoder = prompt_encoder
         self.text_encoder = prompt_encoder
@@ -225,12 +226,46 @@ class StreamDiffusion:
             kind = capi.IN_F16_NCHW
         else:
             raise TypeError(f"unsupported image dtype {x.dtype}")
-        x = x.to(self.device).contiguous()
+        x = x.to(self.device)
+        # VaeImageProcessor.preprocess (re-run inside the reference's StreamDiffusion.__call__): an image that already has
+        # negative values is taken as [-1,1] and NOT normalised again; the encoder's own (x+1)/2 then brings it to [0,1],
+        # which is the range the engine's head expects.  Same host sync (`image.min()`) as the reference; the fused u8 entry
+        # (step_u8, what lib/pipeline.py's __call__ uses) never comes through here.
+        if bool(x.min() < 0):
+            x = x * 0.5 + 0.5
+        x = x.contiguous()
         out = torch.empty((1, 3, self.height, self.width), dtype=torch.float16, device=self.device)
+        t0 = self._tick()
         capi.check(self._lib.b2sd_step_ex(self._handle, x.data_ptr(), kind, x.shape[-2], x.shape[-1], out.data_ptr(),
                                           capi.OUT_F16_NCHW, self._stream()), "b2sd_step_ex")
+        self._tock(t0)
         self.prev_image_result = out
         return out
+
+    # ---- inference_time_ema (StreamDiffusion.__call__ times every frame with CUDA events and keeps
+    # ema = 0.9 ema + 0.1 dt; external code reads the attribute).  The reference pays a device-wide synchronize per frame for
+    # it; here the events are read one frame late, so nothing on the path blocks.
+    def _tick(self):
+        if self._ev is None:
+            self._ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(2)]
+            self._ev_pending = None
+            self._ev_idx = 0
+        if self._ev_pending is not None:
+            e0, e1 = self._ev_pending
+            if e1.query():
+                self.inference_time_ema = 0.9 * self.inference_time_ema + 0.1 * (e0.elapsed_time(e1) / 1000.0)
+                self._ev_pending = None
+        if self._ev_pending is not None:
+            return None            # previous frame still in flight: skip this sample rather than wait
+        pair = self._ev[self._ev_idx]
+        self._ev_idx ^= 1
+        pair[0].record(torch.cuda.current_stream(self.device))
+        return pair
+
+    def _tock(self, pair):
+        if pair is not None:
+            pair[1].record(torch.cuda.current_stream(self.device))
+            self._ev_pending = pair
 
     @torch.no_grad()
     def step_u8(self, frame_nhwc: torch.Tensor) -> torch.Tensor:
@@ -241,8 +276,10 @@ class StreamDiffusion:
             raise TypeError("expected a CUDA uint8 tensor shaped (1,H,W,3)")
         frame_nhwc = frame_nhwc.contiguous()
         out = torch.empty((1, 3, self.height, self.width), dtype=torch.uint8, device=self.device)
+        t0 = self._tick()
         capi.check(self._lib.b2sd_step(self._handle, frame_nhwc.data_ptr(), frame_nhwc.shape[1], frame_nhwc.shape[2],
                                        out.data_ptr(), self._stream()), "b2sd_step")
+        self._tock(t0)
         return out
 
     def step_u8_into(self, frame_nhwc: torch.Tensor, out: torch.Tensor) -> torch.Tensor:

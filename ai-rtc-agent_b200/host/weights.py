@@ -55,10 +55,11 @@ def load_taesd(repo_dir: str) -> Dict[str, torch.Tensor]:
     raise FileNotFoundError(f"no TAESD safetensors under {repo_dir}")
 
 
-def fuse_lora(unet_sd: Dict[str, torch.Tensor], lora_sd: Dict[str, torch.Tensor], scale: float = 1.0) -> int:
+def fuse_lora(unet_sd: Dict[str, torch.Tensor], lora_sd: Dict[str, torch.Tensor], scale: float = 1.0, strict: bool = True) -> int:
     """W += scale * (alpha / rank) * up @ down for every UNet module the LoRA names (diffusers/peft key styles
     `...to_q.lora_A.weight` / `lora.down.weight`, and kohya `lora_unet_*`).  Returns the number of fused layers.
-    This is the weight-prep step the reference performs with pipe.fuse_lora() before building engines."""
+    This is the weight-prep step the reference performs with pipe.fuse_lora() before building engines.  strict (default):
+    every UNet LoRA pair must land on a parameter, otherwise KeyError."""
     pairs: Dict[str, Dict[str, torch.Tensor]] = {}
     for k, v in lora_sd.items():
         base = None
@@ -78,6 +79,7 @@ def fuse_lora(unet_sd: Dict[str, torch.Tensor], lora_sd: Dict[str, torch.Tensor]
         pairs.setdefault(base, {})[role] = v
     index = {k[: -len(".weight")].replace(".", "_"): k for k in unet_sd if k.endswith(".weight")}
     fused = 0
+    unmatched = []
     for base, d in pairs.items():
         if "up" not in d or "down" not in d:
             continue
@@ -88,6 +90,8 @@ def fuse_lora(unet_sd: Dict[str, torch.Tensor], lora_sd: Dict[str, torch.Tensor]
         name = name.replace(".processor", "").replace("to_out_lora", "to_out.0").replace("_lora", "")
         key = name + ".weight" if (name + ".weight") in unet_sd else index.get(name.replace(".", "_"))
         if key is None:
+            if not base.startswith(("lora_te_", "text_encoder.", "lora_te1_", "lora_te2_")):   # text-encoder LoRA: not on this path
+                unmatched.append(base)
             continue
         up, down = d["up"].float(), d["down"].float()
         rank = down.shape[0]
@@ -96,6 +100,9 @@ def fuse_lora(unet_sd: Dict[str, torch.Tensor], lora_sd: Dict[str, torch.Tensor]
         w = unet_sd[key]
         unet_sd[key] = (w.float() + delta.reshape(w.shape)).to(w.dtype)
         fused += 1
+    if strict and (fused == 0 or unmatched):
+        # a LoRA that silently does not apply leaves e.g. SD-1.5 un-distilled while it is run at 4 steps
+        raise KeyError(f"LoRA fusing matched {fused} of {fused + len(unmatched)} UNet modules; unmatched (first 5): {unmatched[:5]}")
     return fused
 
 

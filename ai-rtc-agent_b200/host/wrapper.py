@@ -132,7 +132,10 @@ class StreamDiffusionWrapper:
                     use_lcm_lora, cfg_type) -> StreamDiffusion:
         arch, unet_sd, vae_sd, repo = resolve_weights(model_id_or_path, vae_id, lcm_lora_id, use_lcm_lora, lora_dict,
                                                       self.sd_turbo)
-        encoder = make_prompt_encoder(repo, arch.cross_attention_dim, self.device)
+        import os
+        from .weights import ALLOW_SYNTHETIC_ENV
+        encoder = make_prompt_encoder(repo, arch.cross_attention_dim, self.device,
+                                      allow_synthetic=bool(os.getenv(ALLOW_SYNTHETIC_ENV)) or model_id_or_path.startswith(("tiny", "synthetic")))
         return StreamDiffusion(arch, unet_sd, vae_sd, t_index_list, encoder, torch_dtype=self.dtype, width=self.width,
                                height=self.height, do_add_noise=do_add_noise,
                                use_denoising_batch=self.use_denoising_batch, frame_buffer_size=self.frame_buffer_size,

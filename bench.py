@@ -5,6 +5,7 @@ only, no per-step collective).
 
   python bench.py --gpus N --steps K --warmup W            # this repo (sm_100a engine through the public API)
   python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (fp32 oracle on host cores)
+  python bench.py --impl library --steps K ...             # torch fp16 library path (cuDNN + SDPA, CUDA graph) on the same GPU
 
 A "step" is one frame through StreamDiffusionPipeline.__call__.  `value` is timed on the device with the
 input frame already resident in HBM; `e2e` includes, every step, the pinned-host -> device copy of the frame
@@ -49,6 +50,83 @@ def select_workload(key: str) -> None:
     w = WORKLOADS[key]
     MODEL_ID, T_INDEX_LIST, METRIC, GFLOP_PER_FRAME, WORKLOAD = w["model"], w["t"], w["metric"], w["gflop"], w["name"]
     H = W = w["hw"]
+
+
+def bench_config(world: int) -> dict:
+    """One config dict for every arm (the driver compares the arms' `config` keys)."""
+    return {"workload": WORKLOAD, "t_index_list": T_INDEX_LIST, "weights": "seeded synthetic (no checkpoint offline)",
+            "parallelism": f"dp{world}: one independent stream per GPU, NCCL weight broadcast at init only",
+            "l2": "UNet weights (1.73 GB) are re-streamed from HBM every step (>> 126 MB L2); 64-frame input ring",
+            "model": MODEL_ID}
+
+
+def physical_cores() -> int:
+    """Physical cores of the box (torchrun exports OMP_NUM_THREADS=1, which would hobble the CPU arm to one thread)."""
+    try:
+        pairs = set()
+        phys = core = None
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("physical id"):
+                    phys = line.split(":")[1].strip()
+                elif line.startswith("core id"):
+                    core = line.split(":")[1].strip()
+                elif not line.strip():
+                    if phys is not None and core is not None:
+                        pairs.add((phys, core))
+                    phys = core = None
+        if pairs:
+            return len(pairs)
+    except OSError:
+        pass
+    return max(1, (os.cpu_count() or 2) // 2)
+
+
+def pin_to_gpu_numa_node(dev_index: int):
+    """Bind this rank's host threads to the CPUs of its GPU's NUMA node (pinned-memory copies and launches then stay
+    local).  Returns a short description for the JSON line, or None when the topology files are not readable."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(dev_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus), "pci": bdf}
+    except Exception:   # noqa: BLE001 - best effort
+        return None
+
+
+def nccl_log_summary(log_glob: str):
+    """What NCCL itself reported at init (NCCL_DEBUG=INFO written to NCCL_DEBUG_FILE): ranks, version, transports."""
+    import glob
+    import re
+    nranks, version, nvls, p2p = set(), None, False, False
+    for path in glob.glob(log_glob):
+        try:
+            with open(path, errors="replace") as f:
+                for line in f:
+                    m = re.search(r"nranks (\d+)", line)
+                    if m and "Init COMPLETE" in line:
+                        nranks.add(int(m.group(1)))
+                    m = re.search(r"NCCL version ([0-9.]+)", line)
+                    if m:
+                        version = m.group(1)
+                    nvls |= "NVLS" in line
+                    p2p |= "P2P" in line
+        except OSError:
+            pass
+    return {"init_complete_nranks": sorted(nranks), "version": version, "nvls_seen": nvls, "p2p_seen": p2p, "log": log_glob}
 
 
 def measured_peaks():
@@ -117,7 +195,10 @@ def run_oracle(steps: int, warmup: int, budget_s: float):
     from oracle import stream as ostream
     from oracle import unet as ounet
     from oracle import weights as ow
-    threads = torch.get_num_threads()   # torch's default = physical cores; oversubscribing the SMT siblings is slower
+    # every physical core, set explicitly: under torchrun OMP_NUM_THREADS=1 would otherwise leave this arm single-threaded
+    # (oversubscribing the SMT siblings is slower, so not os.cpu_count())
+    threads = min(physical_cores(), len(os.sched_getaffinity(0)))
+    torch.set_num_threads(threads)
     cfg = ounet.config_for(MODEL_ID)
     usd = ow.to_float(ow.make_unet_weights(cfg))
     vsd = ow.to_float(ow.make_taesd_weights())
@@ -155,7 +236,7 @@ def main_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": r["fps"], "unit": "frames/s", "n_gpus": args.gpus,
             "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "t_index_list": T_INDEX_LIST, "weights": "seeded synthetic"},
+            "config": bench_config(max(1, args.gpus)),
             "cpu_baseline": cb,
             "e2e": {"value": r["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -163,12 +244,75 @@ def main_reference(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------------ library arm
+def run_library(steps: int, warmup: int, dev, use_graph: bool = True):
+    """The same frame program through torch's fp16 library kernels (cuDNN convolutions, cuBLAS GEMMs, fused SDPA), the whole
+    frame captured in one CUDA graph: the stand-in for "the reference's TensorRT engines" that can be built offline
+    (lib/wrapper.py:923-925 falls back to plain torch fp16 when TensorRT is unavailable).  oracle/torch_gpu.py."""
+    import torch
+    from oracle import torch_gpu as tg
+    from oracle import unet as ounet
+    from oracle import weights as ow
+    torch.backends.cudnn.benchmark = True
+    cfg = ounet.config_for(MODEL_ID)
+    orc = tg.build(cfg, ow.make_unet_weights(cfg), ow.make_taesd_weights(), T_INDEX_LIST, H,
+                   ow.make_prompt_embeds(cfg.cross_attention_dim), None, torch.float16, str(dev))
+    frame = tg.GraphedFrame(orc, H, use_graph=use_graph)
+    g = torch.Generator().manual_seed(999)
+    ring = [torch.randint(0, 256, (1, H, W, 3), dtype=torch.uint8, generator=g).to(dev) for _ in range(16)]
+    for i in range(max(warmup, 3)):
+        frame(ring[i % 16])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        frame(ring[i % 16])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": 1000.0 / ms, "unit": "frames/s", "ms_per_step": ms, "steps": steps,
+            "kind": "torch %s fp16: oracle modules .half().cuda(), cuDNN conv (benchmark mode) + fused SDPA + cuBLAS, whole frame in "
+                    "one CUDA graph%s" % (torch.__version__, "" if use_graph else " (graph OFF)")}
+
+
+def main_library(args):
+    import torch
+    rank = int(os.getenv("RANK", "0"))
+    if rank != 0:
+        return 0
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl library needs a CUDA device")
+    dev = torch.device("cuda", int(os.getenv("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    r = run_library(args.steps, args.warmup, dev)
+    line = {"impl": "library", "metric": METRIC, "value": r["value"], "unit": "frames/s", "n_gpus": 1, "steps": r["steps"],
+            "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": bench_config(1),
+            "library_baseline": {"value": r["value"], "unit": "frames/s", "kind": r["kind"]}, "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
+def _pct(xs, q):
+    xs = sorted(xs)
+    return xs[min(len(xs) - 1, int(round(q * (len(xs) - 1))))]
+
+
 def main_gpu(args):
+    import gc
     import torch
     import torch.distributed as dist
     os.environ.setdefault("B200SD_SYNTHETIC_WEIGHTS", "1")
-    os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line (NCCL prints its version banner otherwise)
+    world_env = int(os.getenv("WORLD_SIZE", "1"))
+    nccl_glob = None
+    if world_env > 1:
+        # keep stdout to the single JSON line, but keep NCCL's own account of the job: INFO level into per-process files
+        # (a caller-provided NCCL_DEBUG / NCCL_DEBUG_FILE wins)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(ROOT, "gpurun_out", f"nccl_n{world_env}_%h_%p.log"))
+        nccl_glob = os.environ["NCCL_DEBUG_FILE"].replace("%h", "*").replace("%p", "*")
     os.environ["NVENC"] = "1"  # keep the output tensor in HBM (lib/pipeline.py:83,96)
     from ai_rtc_agent_b200.host import dist as bdist
     from ai_rtc_agent_b200.host.pipeline import StreamDiffusionPipeline
@@ -177,6 +321,7 @@ def main_gpu(args):
     rank, world, local = bdist.init()
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    numa = pin_to_gpu_numa_node(local) if not args.no_numa_pin else None
     bdist.load_and_broadcast(MODEL_ID, dev)          # rank 0 materialises, NCCL broadcast, once
     pipe = StreamDiffusionPipeline(MODEL_ID, t_index_list=T_INDEX_LIST, width=W, height=H)
     stream = pipe.model.stream
@@ -191,11 +336,22 @@ def main_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def gather(vals):
+        """list of floats of this rank -> [world][len] on every rank"""
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world == 1:
+            return [t.tolist()]
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [o.tolist() for o in out]
+
     warm = max(args.warmup, 3)
     for i in range(warm):
         pipe(ring_dev[i % 64])
     # ---- device-resident throughput (value)
     sampler = ClockSampler("GPU-" + str(torch.cuda.get_device_properties(dev).uuid)) if rank == 0 else None
+    gc.collect()
+    gc.disable()   # a collection inside a 20-step timed loop is a multi-ms tail on that rank
     barrier()
     if sampler:
         sampler.start()
@@ -205,32 +361,39 @@ def main_gpu(args):
         pipe(ring_dev[(warm + i) % 64])
     e1.record()
     torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    my_ms = e0.elapsed_time(e1)
     barrier()
     clocks = sampler.stop() if sampler else None
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = ms.item()
+    dev_ms = [r[0] for r in gather([my_ms])]
+    ms_total = max(dev_ms)
     value = world * args.steps / (ms_total / 1000.0)
-    # ---- end to end through the public call with host buffers (e2e)
+    # ---- end to end through the public call with host buffers (e2e): pinned host frame -> H2D -> __call__ -> D2H, every step
+    def e2e_step(i):
+        frame = ring_host[(warm + i) % 64].to(dev, non_blocking=True)
+        out = pipe(frame)
+        out_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for i in range(3):
+        e2e_step(i)            # untimed: first use of the pinned ring / copy path on this rank
     lat = []
     barrier()
     t_all = time.perf_counter()
     for i in range(args.steps):
         t0 = time.perf_counter()
-        frame = ring_host[(warm + i) % 64].to(dev, non_blocking=True)
-        out = pipe(frame)
-        out_host.copy_(out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        lat.append(time.perf_counter() - t0)
-    e2e_s = torch.tensor([time.perf_counter() - t_all], device=dev)
+        e2e_step(i)
+        lat.append((time.perf_counter() - t0) * 1000.0)
+    my_e2e_s = time.perf_counter() - t_all
     barrier()
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_fps = world * args.steps / e2e_s.item()
-    p50 = torch.tensor([statistics.median(lat) * 1000.0], device=dev)
-    if world > 1:
-        dist.all_reduce(p50, op=dist.ReduceOp.MAX)
+    gc.enable()
+    per = gather([my_e2e_s, statistics.median(lat), _pct(lat, 0.99), max(lat), float(lat.index(max(lat)))])
+    e2e_s = max(r[0] for r in per)
+    e2e_fps = world * args.steps / e2e_s
+    p50 = max(r[1] for r in per)
+    slowest = max(range(world), key=lambda r: per[r][0])
+    per_rank = [{"rank": r, "device_ms_per_step": dev_ms[r] / args.steps, "e2e_s": per[r][0], "e2e_p50_ms": per[r][1],
+                 "e2e_p99_ms": per[r][2], "e2e_max_ms": per[r][3], "e2e_max_at_step": int(per[r][4])} for r in range(world)]
+    numa_all = gather([float(numa["numa_node"]) if numa else -1.0])
 
     if rank != 0:
         if world > 1:
@@ -248,6 +411,14 @@ def main_gpu(args):
     # streaming as inside the frame graph) -> average launch duration without the host-side gaps of the eager replay
     ig = stream.profile_kind("igemm", iters=20)
     ig_tflops = ig["flops"] / (ig["ms"] * 1e-3) / 1e12
+    kinds = {}
+    for kind in ("tconv", "attn", "groupnorm", "layernorm"):
+        try:
+            r = stream.profile_kind(kind, iters=20)
+            kinds[kind] = {"ms_per_step": round(r["ms"], 4), "launches": r["launches"],
+                           "tflops": round(r["flops"] / (r["ms"] * 1e-3) / 1e12, 1) if r["flops"] else None}
+        except Exception:   # noqa: BLE001 - kind not present in this program
+            pass
     step_ms = ms_total / args.steps
     step_tflops = GFLOP_PER_FRAME * (value / world) / 1e3
     traffic, traffic_note = None, "no ncu capture found under profiles/"
@@ -268,10 +439,19 @@ def main_gpu(args):
         "kernel_algorithmic_gflop_per_step": ig["flops"] / 1e9,
         "step_achieved": step_tflops, "step_frac": step_tflops / peaks["bf16_tflops_sustained"],
         "step_algorithmic_gflop": GFLOP_PER_FRAME,
+        "other_kernels_in_graph": kinds,
         "by_kernel_eager_ms": {k: round(v["ms"], 4) for k, v in sorted(by.items(), key=lambda kv: -kv[1]["ms"])},
     }
-    # ---- CPU baseline (reported, not the target): bounded sample on this box's host cores
-    cpu = None
+    # ---- baselines (reported, not the target), rank 0 at N=1 only: torch fp16 library path on this GPU, fp32 oracle on the host cores
+    cpu = lib = None
+    if world == 1 and not args.no_library_baseline:
+        del ring_dev
+        try:
+            r = run_library(min(args.steps, 100), 3, dev)
+            lib = {"value": r["value"], "unit": "frames/s", "ms_per_step": r["ms_per_step"], "kind": r["kind"],
+                   "ratio": value / r["value"]}
+        except Exception as exc:   # noqa: BLE001 - the baseline must not take the bench line down
+            lib = {"value": None, "error": f"{type(exc).__name__}: {exc}"[:300]}
     if world == 1 and not args.no_cpu_baseline:
         r = run_oracle(steps=2, warmup=1, budget_s=40.0)
         cpu = {"value": r["fps"], "unit": "frames/s", "cores": r["threads"], "kind": "port",
@@ -280,17 +460,21 @@ def main_gpu(args):
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "t_index_list": T_INDEX_LIST, "weights": "seeded synthetic (no checkpoint offline)",
-                   "parallelism": f"dp{world}: one independent stream per GPU, NCCL weight broadcast at init only",
-                   "l2": "UNet weights (1.73 GB) are re-streamed from HBM every step (>> 126 MB L2); 64-frame input ring",
-                   "model": MODEL_ID},
-        "p50_ms": p50.item(),
+        "config": bench_config(world),
+        "p50_ms": p50,
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": H * W * 3, "d2h_bytes_per_step": H * W * 3,
-                "p50_ms": p50.item()},
+                "p50_ms": p50, "p99_ms": max(r[2] for r in per), "max_ms": max(r[3] for r in per), "slowest_rank": slowest,
+                "samples_per_rank": args.steps,
+                "tails_note": None if args.steps >= 100 else f"p99/max come from only {args.steps} samples per rank"},
+        "per_rank": per_rank,
+        "numa": {"pinned": numa is not None, "rank0": numa, "nodes_by_rank": [int(r[0]) for r in numa_all]},
         "gpu_launches": stream.launches_per_step * args.steps,
         "launches_per_step": stream.launches_per_step,
-        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "roofline": roofline, "library_baseline": lib, "cpu_baseline": cpu, "clocks": clocks,
     }
+    if world > 1:
+        line["nccl"] = dict(nccl_log_summary(nccl_glob) if nccl_glob else {}, world_size=world,
+                            backend=dist.get_backend(), collectives_per_step=0)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -302,9 +486,11 @@ if __name__ == "__main__":
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "library"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true")
+    ap.add_argument("--no-numa-pin", action="store_true")
     ap.add_argument("--workload", default="sd-turbo-512", choices=sorted(WORKLOADS))
     a = ap.parse_args()
     select_workload(a.workload)
-    sys.exit(main_reference(a) if a.impl == "reference" else main_gpu(a))
+    sys.exit(main_reference(a) if a.impl == "reference" else (main_library(a) if a.impl == "library" else main_gpu(a)))

@@ -37,7 +37,14 @@ typedef struct {
     int ld;
 } b2sd_act_view;
 
-enum { B2SD_IG_RELU = 1, B2SD_IG_GEGLU = 2 };
+enum {
+    B2SD_IG_RELU = 1,
+    B2SD_IG_GEGLU = 2,
+    B2SD_IG_CONST_W = 16,    /* hint: `w` is never written by a kernel of the stream (packed weights): it may be fetched
+                                before the programmatic-dependency wait of the launch */
+    B2SD_IG_CONST_SRC = 32,  /* same hint for src[] (the V^T GEMM, whose "activation view" is a weight matrix) */
+    B2SD_IG_TCONV = 64       /* run the persistent halo-tile kernel (stride-1 3x3, 64 -> 64 channels: the TAESD body) */
+};
 
 /* conv3x3 / conv1x1 / Linear as one implicit GEMM:
  *   out[row][j] = acc_scale * (sum_seg sum_tap sum_c src[seg](row, tap, c) * w[j][k] + colbias[b][j])

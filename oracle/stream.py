@@ -40,14 +40,14 @@ def boundary_scalings(timestep: int):
     return c_skip, c_out
 
 
-def image_preprocess(x: torch.Tensor, height: int, width: int) -> torch.Tensor:
+def image_preprocess(x: torch.Tensor, height: int, width: int, assume_unit_range: bool = False) -> torch.Tensor:
     """VaeImageProcessor.preprocess for tensor input: 4-D, nearest resize if needed, 2x-1 unless the
     image already has negative values."""
     if x.dim() == 3:
         x = x.unsqueeze(0)
     if x.shape[-2] != height or x.shape[-1] != width:
         x = F.interpolate(x, size=(height, width))
-    if x.min() < 0:
+    if not assume_unit_range and x.min() < 0:
         return x
     return 2.0 * x - 1.0
 
@@ -96,7 +96,29 @@ class StreamOracle:
         self.beta_prod_t_sqrt = torch.stack([(1 - ac[t]).sqrt() for t in self.sub_timesteps]).view(T, 1, 1, 1).repeat_interleave(Fb, 0)
 
     def update_prompt_embeds(self, prompt_embeds: torch.Tensor) -> None:
-        self.prompt_embeds = prompt_embeds.float().reshape(1, prompt_embeds.shape[-2], -1).repeat(self.batch_size, 1, 1)
+        pe = prompt_embeds.reshape(1, prompt_embeds.shape[-2], -1).repeat(self.batch_size, 1, 1)
+        self.prompt_embeds = pe.to(device=self.device, dtype=self.dtype)
+
+    # ---- the same restatement on another device / dtype (oracle/torch_gpu.py: fp32 or fp16 on the GPU through torch's
+    # library kernels).  Everything the per-frame path touches moves; the math is unchanged.
+    device = torch.device("cpu")
+    dtype = torch.float32
+    static_buffers = False      # True: stream state is updated in place (CUDA-graph capture of the frame)
+    assume_unit_range = False   # True: skip the `image.min() < 0` host sync of VaeImageProcessor (CUDA-graph capture)
+
+    def to(self, device, dtype: torch.dtype = torch.float32) -> "StreamOracle":
+        self.device, self.dtype = torch.device(device), dtype
+        mv = lambda t: t.to(device=self.device, dtype=dtype)
+        self.unet_sd = {k: mv(v) for k, v in self.unet_sd.items()}
+        self.vae_sd = {k: mv(v) for k, v in self.vae_sd.items()}
+        for name in ("prompt_embeds", "init_noise", "stock_noise", "c_skip", "c_out", "alpha_prod_t_sqrt", "beta_prod_t_sqrt",
+                     "x_t_latent_buffer"):
+            v = getattr(self, name, None)
+            if v is not None:
+                setattr(self, name, mv(v))
+        if hasattr(self, "sub_timesteps_tensor"):
+            self.sub_timesteps_tensor = self.sub_timesteps_tensor.to(self.device)
+        return self
 
     # ---- lib/wrapper.py:389-407: rebuilds sub_timesteps only; alpha/beta/c_skip/c_out keep the
     # values prepare() derived from the previous list (reference quirk, reproduced on purpose)
@@ -105,7 +127,7 @@ class StreamOracle:
             return
         self.t_list = list(t_index_list)
         self.sub_timesteps = [self.timesteps[t] for t in t_index_list]
-        self.sub_timesteps_tensor = torch.tensor(self.sub_timesteps, dtype=torch.long).repeat_interleave(self.frame_bff_size)
+        self.sub_timesteps_tensor = torch.tensor(self.sub_timesteps, dtype=torch.long).repeat_interleave(self.frame_bff_size).to(self.device)
 
     # ---- per-frame
     def scheduler_step_batch(self, eps: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
@@ -143,16 +165,19 @@ class StreamOracle:
         if T > 1:
             out = x0_batch[-1:]
             if self.do_add_noise:
-                self.x_t_latent_buffer = (self.alpha_prod_t_sqrt[1:] * x0_batch[:-1]
-                                          + self.beta_prod_t_sqrt[1:] * self.init_noise[1:])
+                nxt = self.alpha_prod_t_sqrt[1:] * x0_batch[:-1] + self.beta_prod_t_sqrt[1:] * self.init_noise[1:]
             else:
-                self.x_t_latent_buffer = self.alpha_prod_t_sqrt[1:] * x0_batch[:-1]
+                nxt = self.alpha_prod_t_sqrt[1:] * x0_batch[:-1]
+            if self.static_buffers:
+                self.x_t_latent_buffer.copy_(nxt)   # CUDA-graph replay needs the state at a fixed address
+            else:
+                self.x_t_latent_buffer = nxt
             return out
         return x0_batch
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
         """x: (3,H',W') or (1,3,H',W') float in [0,1] -> (1,3,H,W) float, roughly [-1,1]."""
-        img = image_preprocess(x.float(), self.height, self.width)
+        img = image_preprocess(x.to(device=self.device, dtype=self.dtype), self.height, self.width, self.assume_unit_range)
         x_t = self.encode_image(img)
         x0 = self.predict_x0_batch(x_t)
         out = taesd.decode(self.vae_sd, x0 / taesd.SCALING_FACTOR)

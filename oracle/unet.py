@@ -21,6 +21,7 @@ import torch
 import torch.nn.functional as F
 
 SD = Dict[str, torch.Tensor]
+FUSED_ATTENTION = False   # True: F.scaled_dot_product_attention instead of the explicit softmax(QK^T)V (same math, library kernels)
 
 
 @dataclass(frozen=True)
@@ -146,13 +147,13 @@ def param_count(cfg: UNetConfig) -> int:
 def timestep_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
     """embeddings.py get_timestep_embedding with flip_sin_to_cos=True, freq_shift=0: [cos | sin]."""
     half = dim // 2
-    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
     args = t.float()[:, None] * freqs[None, :]
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
 
 def time_embed(sd: SD, cfg: UNetConfig, t: torch.Tensor) -> torch.Tensor:
-    e = timestep_embedding(t, cfg.block_out_channels[0])
+    e = timestep_embedding(t, cfg.block_out_channels[0]).to(sd["time_embedding.linear_1.weight"].dtype)  # diffusers: t_emb.to(sample.dtype)
     e = F.linear(e, sd["time_embedding.linear_1.weight"], sd["time_embedding.linear_1.bias"])
     return F.linear(F.silu(e), sd["time_embedding.linear_2.weight"], sd["time_embedding.linear_2.bias"])
 
@@ -176,8 +177,11 @@ def attention(sd: SD, p: str, heads: int, x: torch.Tensor, ctx: torch.Tensor) ->
     q = F.linear(x, sd[p + "to_q.weight"]).view(b, n, heads, d).transpose(1, 2)
     k = F.linear(ctx, sd[p + "to_k.weight"]).view(b, -1, heads, d).transpose(1, 2)
     v = F.linear(ctx, sd[p + "to_v.weight"]).view(b, -1, heads, d).transpose(1, 2)
-    s = torch.softmax((q @ k.transpose(-1, -2)) * (d ** -0.5), dim=-1)
-    o = (s @ v).transpose(1, 2).reshape(b, n, c)
+    if FUSED_ATTENTION:   # library leg (torch_gpu.py): flash / memory-efficient SDPA, what diffusers' AttnProcessor2_0 calls
+        o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, n, c)
+    else:
+        s = torch.softmax((q @ k.transpose(-1, -2)) * (d ** -0.5), dim=-1)
+        o = (s @ v).transpose(1, 2).reshape(b, n, c)
     return F.linear(o, sd[p + "to_out.0.weight"], sd[p + "to_out.0.bias"])
 
 

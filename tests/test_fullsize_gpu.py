@@ -1,0 +1,125 @@
+"""Full-size GPU parity for the configurations the CPU oracle cannot reach in test time, and the third independent
+implementation SURVEY.md 8(c) states the u8 tolerance against.
+
+Three implementations of the same frame (identical seeded fp16 weights, prompt embedding, noise, frames):
+  A. this repo's sm_100a engine, through the C ABI (host/stream.py);
+  B. the oracle's functions executed by torch's GPU library kernels in fp32 (TF32 off) -- oracle/torch_gpu.py;
+  C. the same in fp16 with fused SDPA -- what a plain torch/diffusers fp16 deployment of the reference computes.
+B is tied to the CPU oracle at the tiny size (test_gpu_oracle_equals_cpu_oracle), so A-vs-B at 512x512 / 768x768 is parity
+against the oracle at full size.  Tolerances (stated in SURVEY.md 8c, same as tests/test_engine_gpu.py):
+  latents vs fp32:  max|d| <= 2e-2 * max|ref|, cosine >= 0.999;   u8 image: |d| <= 2 on >= 99.9 % of pixels, max <= 8."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _weights(turbo, full=True):
+    from ai_rtc_agent_b200.host import arch as A
+    from oracle import unet as ounet
+    from oracle import weights as ow
+    if full:
+        cfg, arch = (ounet.SD_TURBO, A.SD_TURBO) if turbo else (ounet.SD15, A.SD15)
+    else:
+        cfg, arch = ounet.tiny_config(turbo), (A.TINY_TURBO if turbo else A.TINY_SD15)
+    return cfg, arch, ow.make_unet_weights(cfg), ow.make_taesd_weights(), ow.make_prompt_embeds(cfg.cross_attention_dim)
+
+
+def _engine(arch, usd, vsd, emb, tl, hw):
+    from ai_rtc_agent_b200.host.stream import StreamDiffusion
+    sd = StreamDiffusion(arch, usd, vsd, tl, lambda p: emb, width=hw, height=hw, device="cuda")
+    sd.prepare("p", guidance_scale=0.0)
+    return sd
+
+
+def _rel_cos(got_nhwc, ref_nchw):
+    got = got_nhwc.float().permute(0, 3, 1, 2).cpu()
+    ref = ref_nchw.float().cpu()
+    rel = (got - ref).abs().max().item() / (ref.abs().max().item() + 1e-12)
+    cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
+    return rel, cos
+
+
+def _u8(got, ref):
+    d = (got.cpu().int() - ref.cpu().int()).abs()
+    return (d <= 2).float().mean().item(), d.max().item()
+
+
+def test_gpu_oracle_equals_cpu_oracle(cuda):
+    """B (oracle functions on the GPU, fp32) reproduces the CPU oracle: ties the full-size references to oracle/."""
+    from oracle import pipeline as opipe
+    from oracle import stream as ostream
+    from oracle import torch_gpu as tg
+    from oracle import weights as ow
+    cfg, arch, usd, vsd, emb = _weights(False, full=False)
+    tl = [18, 26, 35, 45]
+    cpu = ostream.StreamOracle(ow.to_float(usd), cfg, ow.to_float(vsd), tl, 128, 128)
+    cpu.prepare(emb.float(), guidance_scale=0.0)
+    cpu.init_noise = cpu.init_noise.half().float()
+    gpu = tg.build(cfg, usd, vsd, tl, 128, emb, cpu.init_noise, torch.float32)
+    for i in range(5):
+        f = ow.make_frame(128, 128, seed=i)
+        a = opipe.frame_to_u8(cpu, f)
+        b = opipe.frame_to_u8(gpu, f.cuda())
+        rel = (gpu.last["eps"].cpu() - cpu.last["eps"]).abs().max().item() / cpu.last["eps"].abs().max().item()
+        d = (a.int() - b.cpu().int()).abs()
+        assert rel < 1e-4 and d.max().item() <= 1 and (d == 0).float().mean().item() > 0.999, (i, rel, d.max().item())
+
+
+@pytest.mark.parametrize("turbo,tl,hw,nframes", [
+    (False, [18, 26, 35, 45], 512, 5),    # BASELINE config 3: SD-1.5 + LCM 4-step, the agent's default (lib/pipeline.py:12,23-36)
+    (False, [18, 26, 35, 45], 768, 4),    # config 5 shape: seq 9216, odd tile extents, whole-grid GroupNorm fallback
+    (True, [32], 512, 3),                 # config 2 (headline), against both library implementations
+])
+def test_three_implementations_full_size(cuda, turbo, tl, hw, nframes):
+    from oracle import pipeline as opipe
+    from oracle import torch_gpu as tg
+    from oracle import weights as ow
+    cfg, arch, usd, vsd, emb = _weights(turbo)
+    sd = _engine(arch, usd, vsd, emb, tl, hw)
+    ref32 = tg.build(cfg, usd, vsd, tl, hw, emb, sd.init_noise, torch.float32)
+    ref16 = tg.build(cfg, usd, vsd, tl, hw, emb, sd.init_noise, torch.float16)
+    for i in range(nframes):
+        f = ow.make_frame(hw, hw, seed=i).cuda()
+        out = sd.step_u8(f)
+        u32 = opipe.frame_to_u8(ref32, f)
+        with tg.fused_attention():
+            u16 = opipe.frame_to_u8(ref16, f)
+        rel, cos = _rel_cos(sd.get_tensor("eps"), ref32.last["eps"])
+        rel16, cos16 = _rel_cos(ref16.last["eps"].permute(0, 2, 3, 1), ref32.last["eps"])
+        f32, m32 = _u8(out, u32)
+        f16, m16 = _u8(out, u16)
+        l32, lm32 = _u8(u16, u32)
+        print(f"{hw}x{hw} T={len(tl)} frame {i}: eps engine-vs-fp32 rel {rel:.2e} cos {cos:.6f} | torch-fp16-vs-fp32 rel {rel16:.2e} | "
+              f"u8 engine-vs-fp32 {f32:.5f}/{m32}  engine-vs-torch-fp16 {f16:.5f}/{m16}  torch-fp16-vs-fp32 {l32:.5f}/{lm32}")
+        assert rel <= 2e-2 and cos >= 0.999, f"frame {i}: eps vs fp32 library run"
+        assert f32 >= 0.999 and m32 <= 8, f"frame {i}: u8 vs fp32 library run"
+        assert f16 >= 0.999 and m16 <= 8, f"frame {i}: u8 vs fp16 torch run (SURVEY 8c tolerance)"
+        if len(tl) > 1:
+            rb, cb = _rel_cos(sd.get_tensor("unet_in")[1:], ref32.x_t_latent_buffer)
+            assert rb <= 2e-2 and cb >= 0.999, f"frame {i}: x_t_latent_buffer"
+
+
+@pytest.mark.parametrize("name,tl,hw", [("sd15_T4_512", [18, 26, 35, 45], 512), ("sd15_T4_768", [18, 26, 35, 45], 768)])
+def test_full_size_golden_fixture(cuda, name, tl, hw):
+    """Committed CPU-oracle fixtures (tests/golden/make_golden_fullsize.py, generated where the oracle has minutes per
+    frame): eps of every stream-batch slot and an 8x-subsampled u8 image for each frame."""
+    import os
+    import numpy as np
+    from oracle import weights as ow
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{name}.npz not generated")
+    gold = np.load(path)
+    cfg, arch, usd, vsd, emb = _weights(False)
+    sd = _engine(arch, usd, vsd, emb, tl, hw)
+    assert np.array_equal(sd.init_noise.float().numpy(), gold["init_noise"].astype(np.float32))
+    st = int(gold["u8_stride"])
+    for i in range(gold["eps"].shape[0]):
+        out = sd.step_u8(ow.make_frame(hw, hw, seed=i).cuda()).cpu().numpy()
+        eps = sd.get_tensor("eps").float().permute(0, 3, 1, 2).numpy()
+        ref = gold["eps"][i].astype(np.float32)
+        rel = np.abs(eps - ref).max() / np.abs(ref).max()
+        d = np.abs(out[:, :, ::st, ::st].astype(np.int32) - gold["u8"][i].astype(np.int32))
+        print(f"{name} frame {i}: eps rel {rel:.2e}; u8 (1/{st} grid) frac(|d|<=2) {(d <= 2).mean():.5f} max {d.max()}")
+        assert rel <= 2e-2 and (d <= 2).mean() >= 0.999 and d.max() <= 8

@@ -206,3 +206,64 @@ def test_linear_swapped_orientation(cuda, m, k, n, bn, splits):
     ops.igemm([(x, 1)], w, out, colbias=bias, res=res, bn=bn, splits=splits, swap=True)
     ref = x.float().reshape(m, k) @ w.float().t() + bias + res.float().reshape(m, n)
     assert_close(out.reshape(m, n), ref, 4e-3, 3e-3, f"swapped linear m={m} k={k} n={n}")
+
+
+@pytest.mark.parametrize("nb,h,w,relu,res", [
+    (1, 16, 8, False, False),      # exactly one 16x8 tile: descriptor / tap-shift sanity
+    (1, 64, 64, True, True),       # TAESD block tail at the latent size: bias + skip + ReLU
+    (1, 256, 256, True, False),    # 512 tiles on 148 persistent CTAs: ring wrap-around, both TMEM accumulators
+    (2, 40, 28, True, True),       # ragged extents (partial tiles in h and w), two images
+    (1, 512, 512, True, True),     # the full-size TAESD body convolution of the 512x512 configs
+])
+def test_tconv_persistent_halo(cuda, nb, h, w, relu, res):
+    """Persistent halo-tile kernel (tconv.cu: resident weights, nine shifted descriptors over one halo tile) against
+    F.conv2d; same tolerance as the tap-by-tap kernel, and bit-identical to it (same fp32 accumulation order per tap)."""
+    ops = _ops()
+    x = _nhwc16(_rand((nb, 64, h, w), cuda, 1))
+    wt = _rand((64, 64, 3, 3), cuda, 2, 1.0 / math.sqrt(9 * 64)).to(torch.float16)
+    bias = _rand((1, 64), cuda, 3).float().contiguous()
+    r = _nhwc16(_rand((nb, 64, h, w), cuda, 4)) if res else None
+    wp = ops.pack_conv_weight(wt)
+    out = torch.full((nb, h, w, 64), float("nan"), dtype=torch.float16, device=cuda)
+    ops.igemm([(x, 9)], wp, out, colbias=bias, res=r, relu=relu, tconv=True)
+    ref = _ref_conv(x, wt, 1) + bias[:, None, None, :]
+    if res:
+        ref = ref + r.float()
+    if relu:
+        ref = ref.relu()
+    assert_close(out, ref, 3e-3, 3e-3, f"tconv nb={nb} {h}x{w} relu={relu} res={res}")
+    base = torch.empty_like(out)
+    ops.igemm([(x, 9)], wp, base, colbias=bias, res=r, relu=relu)
+    assert_close(out, base, 1e-3, 1e-3, "tconv vs tap-by-tap kernel")
+
+
+def test_tconv_rejects_other_shapes(cuda):
+    ops = _ops()
+    x = _nhwc16(_rand((1, 128, 16, 16), cuda, 1))
+    wp = ops.pack_conv_weight(_rand((64, 128, 3, 3), cuda, 2).to(torch.float16))
+    out = torch.empty((1, 16, 16, 64), dtype=torch.float16, device=cuda)
+    with pytest.raises(Exception):
+        ops.igemm([(x, 9)], wp, out, tconv=True)
+
+
+@pytest.mark.parametrize("const_w,const_src", [(True, False), (False, True)])
+@pytest.mark.parametrize("nb,h,w,cin,cout,splits,swap", [
+    (1, 64, 64, 320, 320, 1, False),    # ring deeper than needed for the first pass
+    (1, 16, 16, 1280, 1280, 4, False),  # split-K slices start at different k-blocks
+    (1, 8, 8, 1280, 1280, 8, True),     # swapped orientation: the weight operand sits in the A region
+    (1, 256, 256, 64, 64, 1, False),    # persistent launch: only the first tile's loads are issued early
+])
+def test_conv3x3_early_constant_operand(cuda, nb, h, w, cin, cout, splits, swap, const_w, const_src):
+    """IG_CONST_W / IG_CONST_SRC: the constant operand's first ring pass is requested before griddepcontrol.wait.
+    Result must be bit-identical to the plain launch."""
+    ops = _ops()
+    x = _nhwc16(_rand((nb, cin, h, w), cuda, 1))
+    wt = _rand((cout, cin, 3, 3), cuda, 2, 1.0 / math.sqrt(9 * cin)).to(torch.float16)
+    bias = _rand((nb, cout), cuda, 3).float().contiguous()
+    wp = ops.pack_conv_weight(wt)
+    bn = 256 if swap else 0
+    ref = torch.empty((nb, h, w, cout), dtype=torch.float16, device=cuda)
+    ops.igemm([(x, 9)], wp, ref, colbias=bias, splits=splits, swap=swap, bn=bn)
+    out = torch.full_like(ref, float("nan"))
+    ops.igemm([(x, 9)], wp, out, colbias=bias, splits=splits, swap=swap, bn=bn, const_w=const_w, const_src=const_src)
+    assert torch.equal(out, ref)
