@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(AT_THREADS, (DA == 1 ? 2 : 1)) attn_kernel(con
     uint64_t* p_full = s_empty + 1;
     uint64_t* o_done = p_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
-    float* xch = reinterpret_cast<float*>(bars + 32);          // 512 B pair-exchange scratch: [2][128] fp16 maxima / [128] fp32 sums
+    float* xch = reinterpret_cast<float*>(bars + 32);          // 512 B pair-exchange scratch: [2][128] 16-bit block maxima / [128] fp32 row sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * AT_BQ;
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(AT_THREADS, (DA == 1 ? 2 : 1)) attn_kernel(con
         float m_run = -INFINITY, l_run = 0.f;
         const uint32_t tS = lane_addr + hf * HC;
         const uint32_t tO = lane_addr + BKV + hf * HO;
-        __half* xmax = reinterpret_cast<__half*>(xch);
+        uint16_t* xmax = reinterpret_cast<uint16_t*>(xch);
         auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };
         // one KV block; MASKED is a compile-time flag so that interior blocks carry no per-element compare/select at all
         auto block = [&](int j, auto masked_tag) {
@@ -218,11 +218,15 @@ __global__ void __launch_bounds__(AT_THREADS, (DA == 1 ? 2 : 1)) attn_kernel(con
             tc_fence_before();
             mbar_arrive(s_empty);
             const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-            // pair exchange in fp16, rounded UP so that exp2 arguments stay <= 0 (any common m is a valid softmax shift).
-            const __half mh = __float2half_ru(fmaxf(mx, -60000.f));
-            xmax[hf * AT_BQ + r] = mh;
+            // Pair exchange of the block maximum as the upper 16 bits of its fp32 pattern, rounded toward +inf (any common
+            // m >= the true maximum is a valid softmax shift; exp2 arguments stay <= 0).  Unlike an fp16 exchange this keeps
+            // the fp32 exponent range: |s| > 65504 cannot become +inf and poison the row.  The lower clamp keeps a fully
+            // masked half finite.
+            const uint32_t mb = __float_as_uint(fmaxf(mx, -3.0e38f));
+            const uint16_t me = (uint16_t)((mb & 0x80000000u) ? (mb >> 16) : ((mb + 0xffffu) >> 16));
+            xmax[hf * AT_BQ + r] = me;
             pair_sync();
-            const float mpair = fmaxf(__half2float(mh), __half2float(xmax[(hf ^ 1) * AT_BQ + r]));
+            const float mpair = fmaxf(__uint_as_float((uint32_t)me << 16), __uint_as_float((uint32_t)xmax[(hf ^ 1) * AT_BQ + r] << 16));
             pair_sync();   // both halves have read: the single exchange buffer may be rewritten for the next block
             const float m_new = fmaxf(m_run, mpair * p.scale_log2);
             const float alpha = ex2_approx(m_run - m_new);
@@ -321,382 +325,6 @@ __global__ void __launch_bounds__(AT_THREADS, (DA == 1 ? 2 : 1)) attn_kernel(con
     if (warp == 1) tmem_dealloc(tmem_base, AT_TMEM_COLS);
 }
 
-// ------------------------------------------------------------------------------------------ stream-K variant
-// EXPERIMENTAL, opt-in (B2_ATTN_SK=1; not yet validated on hardware - round-2 work item).
-// The plain kernel gives one CTA a whole (query tile, head) unit; 160 units on 148 SMs (or PDL placement) leave the launch as
-// slow as its doubly loaded SMs (ncu: 141 K of 141 K cycles there, 83 K elsewhere).  Here the (unit, KV block) space is cut
-// into equal contiguous ranges, one per CTA (<= 296 CTAs = two per SM): a CTA walks its range, starting a new "segment"
-// (fresh Q tile, m = -inf, l = 0, O = 0) whenever it crosses into the next unit.  A segment that covers its whole unit
-// writes the output directly; otherwise it writes an fp32 partial (m, l, unnormalised O) and `attn_sk_merge_kernel`
-// combines the <= PMAX partials of each unit (no inter-CTA waiting anywhere).
-struct AttnSkParams {
-    AttnParams a;
-    int nblk;          // KV blocks per unit
-    int qtiles;        // query tiles per (batch, head)
-    int units;         // nb * heads * qtiles; unit = (b * heads + h) * qtiles + qt
-    int per;           // KV blocks per CTA (uniform; the last CTAs may get fewer or none)
-    int pmax;          // partial slots per unit
-    float* part_o;     // [units][pmax][128][64] unnormalised O
-    float2* part_ml;   // [units][pmax][128] (running max in the log2 domain, row sum)
-};
-
-__global__ void __launch_bounds__(AT_THREADS, 2) attn_sk_kernel(const __grid_constant__ AttnSkParams sp) {
-    constexpr int DA = 1, BKV = 128, DP = 64, KVA = 2;
-    constexpr uint32_t Q_BYTES = DA * AT_BQ * 128;
-    constexpr uint32_t K_BYTES = DA * BKV * 128;
-    constexpr uint32_t V_BYTES = KVA * DP * 128;
-    constexpr uint32_t STAGE_BYTES = K_BYTES + V_BYTES;
-    constexpr uint32_t P_BYTES = KVA * AT_BQ * 128;
-    const AttnParams& p = sp.a;
-
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* sQ = smem;
-    uint8_t* sKV = sQ + Q_BYTES;
-    uint8_t* sP = sKV + AT_STAGES * STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
-    uint64_t* q_full = bars;
-    uint64_t* k_full = bars + 1;
-    uint64_t* k_empty = k_full + AT_STAGES;
-    uint64_t* v_full = k_empty + AT_STAGES;
-    uint64_t* v_empty = v_full + AT_STAGES;
-    uint64_t* s_full = v_empty + AT_STAGES;
-    uint64_t* s_empty = s_full + 1;
-    uint64_t* p_full = s_empty + 1;
-    uint64_t* o_done = p_full + 1;
-    uint64_t* q_empty = o_done + 1;    // every QK^T of the segment has retired: the Q tile may be replaced
-    uint64_t* o_free = q_empty + 1;    // the segment's O accumulator has been read out (256 softmax threads)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
-    float* xch = reinterpret_cast<float*>(bars + 32);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nblk = sp.nblk;
-    // all block indices fit 32 bits (checked by the planner); every role walks (u, j) incrementally: no division in the loops
-    const int total = sp.units * nblk;
-    const int g0 = (int)blockIdx.x * sp.per;
-    const int g1 = min(total, g0 + sp.per);
-    const int u0 = g0 / nblk, j0 = g0 - u0 * nblk;
-    // block g = (unit u, KV block j); a segment starts at g0 and wherever j == 0, ends at g1-1 and wherever j == nblk-1
-
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&p.tmq);
-        tma_prefetch_desc(&p.tmk);
-        tma_prefetch_desc(&p.tmv);
-        mbar_init(q_full, 1);
-        for (int s = 0; s < AT_STAGES; ++s) {
-            mbar_init(&k_full[s], 1);
-            mbar_init(&k_empty[s], 1);
-            mbar_init(&v_full[s], 1);
-            mbar_init(&v_empty[s], 1);
-        }
-        mbar_init(s_full, 1);
-        mbar_init(s_empty, AT_SM_THREADS);
-        mbar_init(p_full, AT_SM_THREADS);
-        mbar_init(o_done, 1);
-        mbar_init(q_empty, 1);
-        mbar_init(o_free, AT_SM_THREADS);
-        fence_mbar_init();
-    }
-    if (warp == 1) {
-        tmem_alloc(tmem_slot, AT_TMEM_COLS);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    pdl_launch_dependents();
-    pdl_wait();
-
-    if (g0 < g1) {
-        // unit -> coordinates
-        auto unit_q0 = [&](int u) { return (u % sp.qtiles) * AT_BQ; };
-        auto unit_h = [&](int u) { return (u / sp.qtiles) % p.heads; };
-        auto unit_b = [&](int u) { return u / (sp.qtiles * p.heads); };
-        if (warp == 0) {
-            if (lane == 0) {
-                // ===== TMA producer =====
-                int seg = 0;
-                auto load_q = [&](int u) {
-                    if (seg > 0) mbar_wait(q_empty, (seg - 1) & 1);
-                    mbar_expect_tx(q_full, Q_BYTES);
-                    tma_load_2d(sQ, &p.tmq, q_full, unit_h(u) * DP, unit_b(u) * p.sq + unit_q0(u));
-                    ++seg;
-                };
-                auto load_k = [&](int it, int u, int j) {
-                    const int st = it % AT_STAGES;
-                    mbar_wait(&k_empty[st], ((it / AT_STAGES) & 1) ^ 1);
-                    mbar_expect_tx(&k_full[st], K_BYTES);
-                    tma_load_2d(sKV + st * STAGE_BYTES, &p.tmk, &k_full[st], unit_h(u) * DP, (int)(unit_b(u) * p.k_bstride) + j * BKV);
-                };
-                auto load_v = [&](int it, int u, int j) {
-                    const int st = it % AT_STAGES;
-                    mbar_wait(&v_empty[st], ((it / AT_STAGES) & 1) ^ 1);
-                    uint8_t* sv = sKV + st * STAGE_BYTES + K_BYTES;
-                    mbar_expect_tx(&v_full[st], V_BYTES);
-#pragma unroll
-                    for (int a = 0; a < KVA; ++a)
-                        tma_load_2d(sv + a * (DP * 128), &p.tmv, &v_full[st], (int)(unit_b(u) * p.vt_bstride) + j * BKV + a * 64, unit_h(u) * DP);
-                };
-                load_q(u0);
-                load_k(0, u0, j0);
-                int u = u0, j = j0;
-                for (int g = g0; g < g1; ++g) {
-                    const int it = g - g0;
-                    const bool wrap = j + 1 == nblk;
-                    const int un = wrap ? u + 1 : u, jn = wrap ? 0 : j + 1;
-                    if (g + 1 < g1) load_k(it + 1, un, jn);
-                    load_v(it, u, j);
-                    if (g + 1 < g1 && wrap) load_q(un);   // waits until the current segment's QK^T have retired
-                    u = un; j = jn;
-                }
-            }
-        } else if (warp == 1) {
-            // ===== MMA issuer =====
-            const uint32_t idesc_s = make_idesc_f16(AT_BQ, BKV);
-            const uint32_t idesc_o = make_idesc_f16(AT_BQ, DP);
-            const uint32_t sq_addr = smem_u32(sQ), skv_addr = smem_u32(sKV), sp_addr = smem_u32(sP);
-            int seg_q = 0;   // segments whose Q tile has been consumed so far (q_full phase)
-            int seg_o = 0;   // segments whose first PV has been issued (o_free phase)
-            auto issue_qk = [&](int it, bool start, bool end) {
-                const int st = it % AT_STAGES;
-                if (start) {
-                    mbar_wait(q_full, seg_q & 1);
-                    ++seg_q;
-                }
-                mbar_wait(&k_full[st], (it / AT_STAGES) & 1);
-                mbar_wait(s_empty, (it & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t sk = skv_addr + st * STAGE_BYTES;
-                if (elect_one()) {
-                    const uint64_t dq = make_kmajor_sw128_desc(sq_addr);
-                    const uint64_t dk = make_kmajor_sw128_desc(sk);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16(tmem_base, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
-                    umma_commit(s_full);
-                    umma_commit(&k_empty[st]);
-                    if (end) umma_commit(q_empty);
-                }
-                __syncwarp();
-            };
-            auto issue_pv = [&](int it, bool first) {
-                const int st = it % AT_STAGES;
-                if (first) {
-                    if (seg_o > 0) mbar_wait(o_free, (seg_o - 1) & 1);   // previous segment's O has been read out
-                    ++seg_o;
-                }
-                mbar_wait(&v_full[st], (it / AT_STAGES) & 1);
-                mbar_wait(p_full, it & 1);
-                tc_fence_after();
-                const uint32_t sv = skv_addr + st * STAGE_BYTES + K_BYTES;
-                if (elect_one()) {
-#pragma unroll
-                    for (int a = 0; a < KVA; ++a) {
-                        const uint64_t dp = make_kmajor_sw128_desc(sp_addr + a * (AT_BQ * 128));
-                        const uint64_t dv = make_kmajor_sw128_desc(sv + a * (DP * 128));
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_f16(tmem_base + BKV, dp + 2 * k, dv + 2 * k, idesc_o, (!first || a > 0 || k > 0) ? 1u : 0u);
-                    }
-                    umma_commit(o_done);
-                    umma_commit(&v_empty[st]);
-                }
-                __syncwarp();
-            };
-            int j = j0;
-            issue_qk(0, true, g0 == g1 - 1 || j0 == nblk - 1);
-            for (int g = g0; g < g1; ++g) {
-                const int it = g - g0;
-                const bool start = g == g0 || j == 0;
-                const bool has_next = g + 1 < g1;
-                const int jn = j + 1 == nblk ? 0 : j + 1;
-                const bool next_new = has_next && jn == 0;
-                const bool next_end = g + 1 == g1 - 1 || jn == nblk - 1;
-                if (has_next && !next_new) issue_qk(it + 1, false, next_end);   // overlaps softmax(g)'s exponentials
-                issue_pv(it, start);
-                if (next_new) issue_qk(it + 1, true, next_end);                  // needs the next unit's Q tile: do not hold PV(g) behind it
-                j = jn;
-            }
-        } else {
-            // ===== softmax / correction / per-segment epilogue =====
-            constexpr int HC = BKV / 2, HO = DP / 2;
-            const int q = warp & 3;
-            const int hf = (warp - 2) >> 2;
-            const int r = q * 32 + lane;
-            const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-            const uint32_t tS = lane_addr + hf * HC;
-            const uint32_t tO = lane_addr + BKV + hf * HO;
-            __half* xmax = reinterpret_cast<__half*>(xch);
-            auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };
-            float m_run = -INFINITY, l_run = 0.f;
-            int u = u0, j = j0 - 1;
-            for (int g = g0; g < g1; ++g) {
-                const int it = g - g0;
-                if (++j == nblk) { j = 0; ++u; }
-                const bool first = g == g0 || j == 0;
-                const bool last = g == g1 - 1 || j == nblk - 1;
-                if (first) { m_run = -INFINITY; l_run = 0.f; }
-                const int kv_valid = p.skv - j * BKV;
-                const bool masked = kv_valid < BKV;
-                mbar_wait(s_full, it & 1);
-                tc_fence_after();
-                uint32_t v[HC];
-#pragma unroll
-                for (int c = 0; c < HC; c += 32) tmem_ld32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&v[c]));
-                tmem_ld_wait();
-                if (masked) {
-#pragma unroll
-                    for (int i = 0; i < HC; ++i)
-                        if (hf * HC + i >= kv_valid) v[i] = 0xff800000u;   // -inf: exp2 -> 0, never the maximum
-                }
-                float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-                for (int i = 0; i < HC; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
-                tc_fence_before();
-                mbar_arrive(s_empty);
-                const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-                const __half mh = __float2half_ru(fmaxf(mx, -60000.f));
-                xmax[hf * AT_BQ + r] = mh;
-                pair_sync();
-                const float mpair = fmaxf(__half2float(mh), __half2float(xmax[(hf ^ 1) * AT_BQ + r]));
-                pair_sync();
-                const float m_new = fmaxf(m_run, mpair * p.scale_log2);
-                const float alpha = ex2_approx(m_run - m_new);
-                if (it > 0) mbar_wait(o_done, (it - 1) & 1);   // PV(it-1) retired: P buffer + O are ours
-                float rs4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int c = 0; c < HC; c += 32) {
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float p0 = ex2_approx(__uint_as_float(v[c + i]) * p.scale_log2 - m_new);
-                        const float p1 = ex2_approx(__uint_as_float(v[c + i + 1]) * p.scale_log2 - m_new);
-                        rs4[(i >> 1) & 3] += p0 + p1;
-                        const __half2 hp = __floats2half2_rn(p0, p1);
-                        pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
-                    }
-                    const int cabs = hf * HC + c;
-                    uint8_t* prow = sP + (cabs >> 6) * (AT_BQ * 128);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const uint32_t chunk = ((cabs & 63) >> 3) + u;
-                        *reinterpret_cast<uint4*>(prow + sw128_offset(r, chunk)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-                    }
-                }
-                if (!first) {
-                    const bool need = __any_sync(0xffffffffu, alpha != 1.0f);
-                    if (need) {
-                        uint32_t o[32];
-                        tmem_ld32(tO, o);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st32(tO, o);
-                        tmem_st_wait();
-                    }
-                }
-                l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
-                m_run = m_new;
-                fence_proxy_async_smem();
-                tc_fence_before();
-                mbar_arrive(p_full);
-                if (!last) continue;
-                // ---- segment epilogue
-                pair_sync();
-                if (hf == 1) xch[r] = l_run;
-                pair_sync();
-                const float l_tot = hf == 0 ? l_run + xch[r] : 0.f;
-                pair_sync();
-                if (hf == 0) xch[r] = l_tot;
-                pair_sync();
-                const float l_pair = xch[r];
-                pair_sync();   // the buffer goes back to the fp16 maxima of the next segment
-                mbar_wait(o_done, it & 1);
-                tc_fence_after();
-                uint32_t ov[32];
-                tmem_ld32(tO, ov);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(o_free);   // O is in registers: the next segment may overwrite the accumulator
-                const bool whole = g0 <= u * nblk && j == nblk - 1;   // this CTA holds every KV block of the unit
-                const int row = unit_q0(u) + r;
-                if (whole) {
-                    const float inv_l = 1.0f / l_pair;
-                    if (row < p.sq) {
-                        __half* orow = p.out + ((long)unit_b(u) * p.sq + row) * p.ldo + unit_h(u) * p.d_real;
-#pragma unroll
-                        for (int c8 = 0; c8 < 4; ++c8) {
-                            const int col = hf * HO + 8 * c8;
-                            if (col + 8 <= p.d_real) {
-                                uint4 o;
-                                __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                                for (int i = 0; i < 4; ++i)
-                                    oh[i] = __floats2half2_rn(__uint_as_float(ov[8 * c8 + 2 * i]) * inv_l, __uint_as_float(ov[8 * c8 + 2 * i + 1]) * inv_l);
-                                *reinterpret_cast<uint4*>(orow + col) = o;
-                            }
-                        }
-                    }
-                } else {
-                    const int k = (int)blockIdx.x - (u * nblk) / sp.per;   // this CTA's slot among the unit's parts
-                    float* po = sp.part_o + (((long)u * sp.pmax + k) * AT_BQ + r) * DP + hf * HO;
-#pragma unroll
-                    for (int c4 = 0; c4 < 8; ++c4)
-                        reinterpret_cast<float4*>(po)[c4] = make_float4(__uint_as_float(ov[4 * c4]), __uint_as_float(ov[4 * c4 + 1]),
-                                                                       __uint_as_float(ov[4 * c4 + 2]), __uint_as_float(ov[4 * c4 + 3]));
-                    if (hf == 0) sp.part_ml[((long)u * sp.pmax + k) * AT_BQ + r] = make_float2(m_run, l_pair);
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, AT_TMEM_COLS);
-}
-
-// one CTA per unit, one thread per query row: combine the unit's partials (flash-decoding style)
-__global__ void __launch_bounds__(AT_BQ) attn_sk_merge_kernel(AttnSkParams sp) {
-    pdl_launch_dependents();
-    pdl_wait();
-    const AttnParams& p = sp.a;
-    const int u = blockIdx.x, r = threadIdx.x;
-    const long first = (long)u * sp.nblk, last = first + sp.nblk - 1;
-    const int c_lo = (int)(first / sp.per), c_hi = (int)(last / sp.per);
-    const int parts = c_hi - c_lo + 1;
-    if (parts == 1) return;   // the unit was computed by a single CTA, which wrote the output itself
-    const int row = (u % sp.qtiles) * AT_BQ + r;
-    if (row >= p.sq) return;
-    const int h = (u / sp.qtiles) % p.heads, b = u / (sp.qtiles * p.heads);
-    float m_max = -INFINITY;
-    for (int k = 0; k < parts; ++k) m_max = fmaxf(m_max, sp.part_ml[((long)u * sp.pmax + k) * AT_BQ + r].x);
-    float acc[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-    float l = 0.f;
-    for (int k = 0; k < parts; ++k) {
-        const float2 ml = sp.part_ml[((long)u * sp.pmax + k) * AT_BQ + r];
-        const float w = ex2_approx(ml.x - m_max);
-        l += ml.y * w;
-        const float4* po = reinterpret_cast<const float4*>(sp.part_o + (((long)u * sp.pmax + k) * AT_BQ + r) * 64);
-#pragma unroll
-        for (int c4 = 0; c4 < 16; ++c4) {
-            const float4 v = po[c4];
-            acc[4 * c4] += v.x * w; acc[4 * c4 + 1] += v.y * w; acc[4 * c4 + 2] += v.z * w; acc[4 * c4 + 3] += v.w * w;
-        }
-    }
-    const float inv_l = 1.0f / l;
-    __half* orow = p.out + ((long)b * p.sq + row) * p.ldo + h * p.d_real;
-#pragma unroll
-    for (int c8 = 0; c8 < 8; ++c8) {
-        if (8 * c8 + 8 <= p.d_real) {
-            uint4 o;
-            __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(acc[8 * c8 + 2 * i] * inv_l, acc[8 * c8 + 2 * i + 1] * inv_l);
-            *reinterpret_cast<uint4*>(orow + 8 * c8) = o;
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------ host
 static int encode_2d(CUtensorMap* m, const __half* ptr, long cols, long rows, long ld, int box_cols, int box_rows,
                      const char* what) {
@@ -751,39 +379,6 @@ int attn_plan(const AttnDesc& d, AttnPlan* plan) {
     if (encode_2d(&plan->tmv, d.vt, d.vt_cols, (long)d.heads * d.dp, d.ldvt, 64, d.dp, "vt")) return -1;
     plan->grid = dim3((d.sq + AT_BQ - 1) / AT_BQ, d.heads, d.nb);
     plan->smem = attn_smem_bytes(d.dp / 64, bkv);
-    static const bool sk_on = getenv("B2_ATTN_SK") != nullptr;
-    if (sk_on && d.dp == 64) {
-        const int nblk = (d.skv + 127) / 128, qtiles = (d.sq + AT_BQ - 1) / AT_BQ;
-        const long units = (long)d.nb * d.heads * qtiles, total = units * nblk;
-        if (nblk >= 8 && total >= 1024 && total < (1l << 30)) {   // long self-attention only: the merge must amortise
-            const int slots = 2 * 148;
-            const int per = (int)((total + slots - 1) / slots);
-            int pmax = 1;
-            for (long u = 0; u < units; ++u) {
-                const int parts = (int)((u * nblk + nblk - 1) / per - (u * nblk) / per) + 1;
-                if (parts > pmax) pmax = parts;
-            }
-            static float* pool_o = nullptr;
-            static float2* pool_ml = nullptr;
-            static size_t pool_slots = 0;
-            const size_t need = (size_t)units * pmax;
-            if (need > pool_slots) {   // plan time: never under stream capture
-                if (pool_o) cudaFree(pool_o);
-                if (pool_ml) cudaFree(pool_ml);
-                pool_o = nullptr; pool_ml = nullptr; pool_slots = 0;
-                if (cudaMalloc(&pool_o, need * AT_BQ * 64 * sizeof(float)) != cudaSuccess ||
-                    cudaMalloc(&pool_ml, need * AT_BQ * sizeof(float2)) != cudaSuccess) {
-                    b2_set_error("attn(stream-K): scratch allocation failed (%zu slots)", need);
-                    return -1;
-                }
-                pool_slots = need;
-            }
-            plan->sk = 1;
-            plan->sk_nblk = nblk; plan->sk_qtiles = qtiles; plan->sk_units = (int)units; plan->sk_per = per; plan->sk_pmax = pmax;
-            plan->sk_grid = (int)((total + per - 1) / per);
-            plan->sk_part_o = pool_o; plan->sk_part_ml = pool_ml;
-        }
-    }
     return 0;
 }
 
@@ -793,7 +388,6 @@ int attn_init() {
         cudaError_t e1 = cudaFuncSetAttribute(attn_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaError_t e2 = cudaFuncSetAttribute(attn_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaError_t e3 = cudaFuncSetAttribute(attn_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(attn_sk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
             b2_set_error("cudaFuncSetAttribute(attn) failed");
             return -1;
@@ -813,14 +407,6 @@ int attn_launch(const AttnPlan& plan, cudaStream_t s) {
     p.k_bstride = d.k_bstride; p.vt_bstride = d.vt_bstride;
     p.scale_log2 = (float)(1.4426950408889634 / sqrt((double)d.d_real));
     cudaError_t e;
-    if (plan.sk) {
-        AttnSkParams sp;
-        sp.a = p;
-        sp.nblk = plan.sk_nblk; sp.qtiles = plan.sk_qtiles; sp.units = plan.sk_units; sp.per = plan.sk_per; sp.pmax = plan.sk_pmax;
-        sp.part_o = plan.sk_part_o; sp.part_ml = static_cast<float2*>(plan.sk_part_ml);
-        e = launch_k(attn_sk_kernel, dim3(plan.sk_grid), dim3(AT_THREADS), plan.smem, s, 1, sp);
-        if (e == cudaSuccess) e = launch_k(attn_sk_merge_kernel, dim3(plan.sk_units), dim3(AT_BQ), 0, s, 1, sp);
-    } else
     if (d.dp == 64) e = launch_k(attn_kernel<1, 128>, plan.grid, dim3(AT_THREADS), plan.smem, s, 1, p);
     else if (d.dp == 128) e = launch_k(attn_kernel<2, 128>, plan.grid, dim3(AT_THREADS), plan.smem, s, 1, p);
     else e = launch_k(attn_kernel<3, 64>, plan.grid, dim3(AT_THREADS), plan.smem, s, 1, p);

@@ -32,11 +32,6 @@ struct AttnPlan {
     AttnDesc d;
     dim3 grid;
     size_t smem;
-    // stream-K variant (experimental, B2_ATTN_SK=1): equal contiguous ranges of (unit, KV block) per CTA + a merge launch
-    int sk;                 // 0 = plain kernel
-    int sk_nblk, sk_qtiles, sk_units, sk_per, sk_pmax, sk_grid;
-    float* sk_part_o;       // process-wide scratch (launches are stream ordered; every launch consumes its own partials)
-    void* sk_part_ml;
 };
 
 int attn_plan(const AttnDesc& d, AttnPlan* plan);

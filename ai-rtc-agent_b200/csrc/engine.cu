@@ -45,7 +45,8 @@ struct Act {
 };
 
 struct Raw {  // a loaded parameter, fp16 on device (+ host fp32 copy for 1-D tensors)
-    __half* p = nullptr;
+    __half* p = nullptr;      // null once released (pack-only parameters after the first successful prepare)
+    bool pack_only = false;   // only ever read by the packing kernels (3x3 / shortcut convs, q/k/v, GEGLU, Cin<=4 convs)
     std::vector<int64_t> shape;
     std::vector<float> host;
     long numel() const {
@@ -205,11 +206,15 @@ struct b2sd_engine {
     b2sd_config cfg{};
     int lh = 0, lw = 0;  // latent extents
     std::map<std::string, Raw> raw;
-    Arena weights{256u << 20};   // raw + packed parameters (live for the engine's lifetime)
+    Arena weights{256u << 20};   // packed parameters + the raw ones kernels read directly (live for the engine's lifetime)
+    Arena raw_only{256u << 20};  // raw parameters that only feed the packing kernels: released after the first prepare
+    bool raw_released = false;
+    bool imported = false;       // parameters came from a packed blob (b2sd_import_packed)
     Arena state{16u << 20};      // stream state + small persistent vectors
     Arena prog{512u << 20};      // activations / per-program buffers (reset at prepare)
     std::map<std::string, __half*> packed;   // cache of packed weight matrices
     std::map<std::string, float*> fvec;      // cache of fp32 vectors
+    std::map<std::string, size_t> packed_bytes, fvec_bytes;   // their sizes (b2sd_export_packed)
     std::map<std::string, int*> perms;
 
     // persistent stream state (StreamDiffusion attributes)
@@ -277,6 +282,7 @@ struct b2sd_engine {
         if (!d) return nullptr;
         if (cudaMemcpy(d, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
         fvec[ck] = d;
+        fvec_bytes[ck] = host.size() * sizeof(float);
         return d;
     }
 
@@ -286,10 +292,12 @@ struct b2sd_engine {
         if (it != fvec.end()) return it->second;
         const Raw* r = get(key);
         if (!r) return nullptr;
+        if (!r->p) { b2_set_error("parameter '%s' was released after the first prepare and is not in the packed cache", key.c_str()); return nullptr; }
         const int cout = (int)r->shape[0], cin = (int)r->shape[1];
         float* d = static_cast<float*>(weights.alloc((size_t)cin * 9 * cout * sizeof(float)));
         if (!d || smallconv_prep_launch(r->p, d, cout, cin, s)) return nullptr;
         fvec["sw:" + key] = d;
+        fvec_bytes["sw:" + key] = (size_t)cin * 9 * cout * sizeof(float);
         return d;
     }
 
@@ -310,11 +318,13 @@ struct b2sd_engine {
         for (auto& g : segs) {
             const Raw* r = get(g.key);
             if (!r) return nullptr;
+            if (!r->p) { b2_set_error("parameter '%s' was released after the first prepare and is not in the packed cache", g.key.c_str()); return nullptr; }
             const int cin_total = (int)r->shape[1];
             if (pack_conv_weight_launch(r->p, dst, K, koff, rows, cin_total, g.taps, g.c0, g.cn, s)) return nullptr;
             koff += g.taps * g.cn;
         }
         packed[name] = dst;
+        packed_bytes[name] = (size_t)rows_pad * K * 2;
         return dst;
     }
     // rows gathered from one or more [*, K] matrices: spec = list of (key, perm)
@@ -332,6 +342,7 @@ struct b2sd_engine {
         for (auto& p : parts) {
             const Raw* r = get(p.first);
             if (!r) return nullptr;
+            if (!r->p) { b2_set_error("parameter '%s' was released after the first prepare and is not in the packed cache", p.first.c_str()); return nullptr; }
             int* dperm = static_cast<int*>(weights.alloc(p.second.size() * sizeof(int)));
             if (!dperm) return nullptr;
             cudaMemcpyAsync(dperm, p.second.data(), p.second.size() * sizeof(int), cudaMemcpyHostToDevice, s);
@@ -340,6 +351,7 @@ struct b2sd_engine {
             r0 += p.second.size();
         }
         packed[name] = dst;
+        packed_bytes[name] = rows_pad * K * 2;
         return dst;
     }
 
@@ -1017,6 +1029,16 @@ int b2sd_destroy(b2sd_handle h) {
     return 0;
 }
 
+// Parameters whose raw layout no kernel reads: they are re-laid-out once by pack_conv / pack_rows / small_w.
+static bool is_pack_only(const std::string& key, const int64_t* shape, int ndim) {
+    auto has = [&](const char* t) { return key.find(t) != std::string::npos; };
+    if (ndim == 4 && shape[2] == 3) return true;                       // every 3x3 convolution (incl. the Cin <= 4 ones)
+    if (ndim == 4 && has("conv_shortcut.weight")) return true;         // packed into the conv2 rows
+    if (ndim == 2 && (has(".to_q.weight") || has(".to_k.weight") || has(".to_v.weight"))) return true;   // per-head gather
+    if (ndim == 2 && has("ff.net.0.proj.weight")) return true;         // GEGLU value/gate interleave
+    return false;
+}
+
 int b2sd_load_tensor(b2sd_handle h, const char* key, const void* ptr, int dtype, const int64_t* shape, int ndim) {
     if (!h || !key || !ptr || ndim < 1 || ndim > 4) {
         b2_set_error("b2sd_load_tensor: bad argument");
@@ -1025,16 +1047,22 @@ int b2sd_load_tensor(b2sd_handle h, const char* key, const void* ptr, int dtype,
     Raw r;
     r.shape.assign(shape, shape + ndim);
     const long n = r.numel();
+    if (h->raw_released) {
+        b2_set_error("b2sd_load_tensor(%s): the pack-only raw weights were released after b2sd_prepare; create a new engine to "
+                     "load different parameters (or set B2_KEEP_RAW=1 before the first prepare)", key);
+        return -1;
+    }
+    r.pack_only = is_pack_only(key, shape, ndim);
     auto old = h->raw.find(key);
     if (old != h->raw.end()) {
         // Reload of a parameter (e.g. a LoRA swap): everything derived from the old values is stale.  The packed / fp32
         // caches are keyed by parameter name, so drop them all (they are rebuilt by the next b2sd_prepare); a same-shape
         // reload overwrites the device copy in place instead of growing the bump arena.
-        h->packed.clear();
-        h->fvec.clear();
+        h->packed.clear(); h->packed_bytes.clear();
+        h->fvec.clear(); h->fvec_bytes.clear();
         if (old->second.shape == r.shape) r.p = old->second.p;
     }
-    if (!r.p) r.p = static_cast<__half*>(h->weights.alloc((size_t)n * 2));
+    if (!r.p) r.p = static_cast<__half*>((r.pack_only ? h->raw_only : h->weights).alloc((size_t)n * 2));
     if (!r.p) {
         b2_set_error("b2sd_load_tensor: cudaMalloc failed for %s", key);
         return -1;
@@ -1112,6 +1140,164 @@ int b2sd_prepare(b2sd_handle h, const void* prompt_embeds, const float* timestep
     TRY(h->run(h->prog_prompt, s));
     TRY(refresh_time(h, s));
     CUDA_OK(cudaStreamSynchronize(s));
+    // Every pack-only parameter now exists in its kernel-native layout: drop the raw copies (about half of the UNet's
+    // 1.73 GB).  Later prepares hit the packed caches and never touch them.
+    static const bool keep_raw = getenv("B2_KEEP_RAW") != nullptr;
+    if (!keep_raw && !h->raw_released) {
+        for (auto& kv : h->raw)
+            if (kv.second.pack_only) kv.second.p = nullptr;
+        h->raw_only.release();
+        h->raw_released = true;
+    }
+    return 0;
+}
+
+// ---- packed-weight blob (replaces the reference's TensorRT engine files, lib/wrapper.py:593-597, 896-910) -----------------
+// Layout: "B2SDPACK" u32 version, b2sd_config, u32 count, then per entry
+//   u8 kind (0 raw parameter, 1 packed fp16 matrix, 2 fp32 vector) | u32 name length | name | u32 ndim | i64 shape[ndim] |
+//   u64 payload bytes (0 for a raw pack-only parameter: only its shape is needed) | payload
+extern "C++" {
+namespace {
+struct BlobWriter {
+    FILE* f;
+    bool ok = true;
+    void put(const void* p, size_t n) { if (ok && n && fwrite(p, 1, n, f) != n) ok = false; }
+    template <class T> void pod(const T& v) { put(&v, sizeof(T)); }
+    void str(const std::string& v) { pod((uint32_t)v.size()); put(v.data(), v.size()); }
+};
+struct BlobReader {
+    FILE* f;
+    bool ok = true;
+    void get(void* p, size_t n) { if (ok && n && fread(p, 1, n, f) != n) ok = false; }
+    template <class T> T pod() { T v{}; get(&v, sizeof(T)); return v; }
+    std::string str() { uint32_t n = pod<uint32_t>(); if (!ok || n > 4096) { ok = false; return ""; } std::string v(n, 0); get(&v[0], n); return v; }
+};
+}  // namespace
+}  // extern "C++"
+
+int b2sd_export_packed(b2sd_handle h, const char* path) {
+    if (!h || !h->built || !path) {
+        b2_set_error("b2sd_export_packed: call b2sd_prepare first");
+        return -1;
+    }
+    FILE* f = fopen(path, "wb");
+    if (!f) {
+        b2_set_error("b2sd_export_packed: cannot open %s", path);
+        return -1;
+    }
+    BlobWriter w{f};
+    w.put("B2SDPACK", 8);
+    w.pod((uint32_t)1);
+    b2sd_config cfg = h->cfg;
+    cfg.batch = 0; cfg.height = 0; cfg.width = 0; cfg.use_cuda_graph = 0; cfg.do_add_noise = 0;   // the blob is independent of these
+    w.pod(cfg);
+    w.pod((uint32_t)(h->raw.size() + h->packed_bytes.size() + h->fvec_bytes.size()));
+    std::vector<char> host;
+    auto payload = [&](const void* dptr, size_t bytes) {
+        w.pod((uint64_t)bytes);
+        if (!bytes) return true;
+        host.resize(bytes);
+        if (cudaMemcpy(host.data(), dptr, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+        w.put(host.data(), bytes);
+        return true;
+    };
+    bool copy_ok = true;
+    for (auto& kv : h->raw) {
+        const Raw& r = kv.second;
+        w.pod((uint8_t)0); w.str(kv.first);
+        w.pod((uint32_t)r.shape.size());
+        for (auto d : r.shape) w.pod((int64_t)d);
+        copy_ok &= payload(r.p, (r.pack_only || !r.p) ? 0 : (size_t)r.numel() * 2);
+    }
+    for (auto& kv : h->packed_bytes) {
+        w.pod((uint8_t)1); w.str(kv.first); w.pod((uint32_t)0);
+        copy_ok &= payload(h->packed[kv.first], kv.second);
+    }
+    for (auto& kv : h->fvec_bytes) {
+        w.pod((uint8_t)2); w.str(kv.first); w.pod((uint32_t)0);
+        copy_ok &= payload(h->fvec[kv.first], kv.second);
+    }
+    const bool ok = w.ok && copy_ok && fclose(f) == 0;
+    if (!ok) {
+        b2_set_error("b2sd_export_packed: write to %s failed", path);
+        remove(path);
+        return -1;
+    }
+    return 0;
+}
+
+int b2sd_import_packed(b2sd_handle h, const char* path) {
+    if (!h || !path) {
+        b2_set_error("b2sd_import_packed: null argument");
+        return -1;
+    }
+    if (!h->raw.empty()) {
+        b2_set_error("b2sd_import_packed: the engine already holds parameters");
+        return -1;
+    }
+    FILE* f = fopen(path, "rb");
+    if (!f) {
+        b2_set_error("b2sd_import_packed: cannot open %s", path);
+        return -1;
+    }
+    BlobReader rd{f};
+    char magic[8];
+    rd.get(magic, 8);
+    const uint32_t version = rd.pod<uint32_t>();
+    b2sd_config cfg = rd.pod<b2sd_config>();
+    bool same = rd.ok && memcmp(magic, "B2SDPACK", 8) == 0 && version == 1 && cfg.cross_attention_dim == h->cfg.cross_attention_dim &&
+                cfg.layers_per_block == h->cfg.layers_per_block && cfg.norm_groups == h->cfg.norm_groups && cfg.ctx_tokens == h->cfg.ctx_tokens;
+    for (int i = 0; i < 4 && same; ++i)
+        same = cfg.block_out_channels[i] == h->cfg.block_out_channels[i] && cfg.heads[i] == h->cfg.heads[i] && cfg.down_attn[i] == h->cfg.down_attn[i];
+    if (!same) {
+        fclose(f);
+        b2_set_error("b2sd_import_packed: %s is not a packed-weight blob of this architecture", path);
+        return -1;
+    }
+    const uint32_t count = rd.pod<uint32_t>();
+    std::vector<char> host;
+    for (uint32_t i = 0; i < count && rd.ok; ++i) {
+        const uint8_t kind = rd.pod<uint8_t>();
+        const std::string name = rd.str();
+        const uint32_t ndim = rd.pod<uint32_t>();
+        Raw r;
+        for (uint32_t d = 0; d < ndim && d < 8; ++d) r.shape.push_back(rd.pod<int64_t>());
+        const uint64_t bytes = rd.pod<uint64_t>();
+        if (!rd.ok || bytes > ((uint64_t)1 << 32)) { rd.ok = false; break; }
+        void* dptr = nullptr;
+        if (bytes) {
+            host.resize(bytes);
+            rd.get(host.data(), bytes);
+            dptr = h->weights.alloc(bytes);
+            if (!rd.ok || !dptr || cudaMemcpy(dptr, host.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) { rd.ok = false; break; }
+        }
+        if (kind == 0) {
+            r.p = static_cast<__half*>(dptr);
+            r.pack_only = bytes == 0;
+            if (ndim == 1 && bytes) {
+                const __half* hp = reinterpret_cast<const __half*>(host.data());
+                r.host.resize(bytes / 2);
+                for (size_t k = 0; k < r.host.size(); ++k) r.host[k] = __half2float(hp[k]);
+            }
+            h->raw[name] = std::move(r);
+        } else if (kind == 1) {
+            h->packed[name] = static_cast<__half*>(dptr);
+            h->packed_bytes[name] = bytes;
+        } else if (kind == 2) {
+            h->fvec[name] = static_cast<float*>(dptr);
+            h->fvec_bytes[name] = bytes;
+        } else {
+            rd.ok = false;
+        }
+    }
+    fclose(f);
+    if (!rd.ok) {
+        b2_set_error("b2sd_import_packed: %s is truncated or corrupt", path);
+        return -1;
+    }
+    h->raw_released = true;   // there never was a raw copy of the pack-only parameters
+    h->imported = true;
+    h->built = false;
     return 0;
 }
 

@@ -207,9 +207,15 @@ __global__ void __launch_bounds__(IG_THREADS, IG_THREADS <= 192 ? 2 : 1) igemm_k
         }
     };
     // normal: pixels -> A region (M side), weights -> B region.  swapped: weights (128 output channels) -> A region, pixels -> B
-    auto load_src = [&](int stage, const KCursor& c, int mt) {   // the 4-D "activation view" operand (tmA)
-        const int w0 = (mt % p.tiles_w) * p.tw, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
-        const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
+    struct TileOrg { int w0, h0, n0; };
+    auto tile_origin = [&](int mt) {   // integer divisions: once per M tile, never per k-block (the producer's issue rate matters)
+        TileOrg t;
+        t.w0 = (mt % p.tiles_w) * p.tw * p.stride;
+        t.h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th * p.stride;
+        t.n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
+        return t;
+    };
+    auto load_src = [&](int stage, const KCursor& c, const TileOrg& t) {   // the 4-D "activation view" operand (tmA)
         uint8_t* sa = smem + (size_t)stage * stage_bytes;
         int dy = 0, dx = 0;
         if (p.seg_ntap[c.seg] == 9) {
@@ -217,7 +223,7 @@ __global__ void __launch_bounds__(IG_THREADS, IG_THREADS <= 192 ? 2 : 1) igemm_k
             dx = c.tap % 3 - 1;
         }
         tma_load_4d(p.swap ? sa + IG_BM * IG_BK * 2 : sa, &p.tmA[c.seg], &full_bar[stage], p.seg_c0[c.seg] + c.cb * IG_BK,
-                    w0 * p.stride + dx, h0 * p.stride + dy, n0);
+                    t.w0 + dx, t.h0 + dy, t.n0);
     };
     auto load_w = [&](int stage, int kb) {                        // the 2-D "weight matrix" operand (tmB)
         uint8_t* sa = smem + (size_t)stage * stage_bytes;
@@ -232,10 +238,11 @@ __global__ void __launch_bounds__(IG_THREADS, IG_THREADS <= 192 ? 2 : 1) igemm_k
         if (lane == 0 && (p.epi.flags & (IG_CONST_B | IG_CONST_A)) && (int)blockIdx.x < num_mtiles && p.dbg_mode == 0) {
             early = min(p.num_stages, kb_end - kb_begin);
             KCursor c = cursor_at(kb_begin);
+            const TileOrg t0 = tile_origin(blockIdx.x);
             for (int s = 0; s < early; ++s) {
                 mbar_expect_tx(&full_bar[s], p.a_bytes + p.b_bytes);
                 if (p.epi.flags & IG_CONST_B) load_w(s, kb_begin + s);
-                if (p.epi.flags & IG_CONST_A) load_src(s, c, blockIdx.x);
+                if (p.epi.flags & IG_CONST_A) load_src(s, c, t0);
                 cursor_next(c);
             }
         }
@@ -250,8 +257,11 @@ __global__ void __launch_bounds__(IG_THREADS, IG_THREADS <= 192 ? 2 : 1) igemm_k
             // ===== TMA producer =====
             int stage = 0;
             uint32_t phase = 0;
+            const bool early_a = (p.epi.flags & IG_CONST_A) != 0, early_b = (p.epi.flags & IG_CONST_B) != 0;
             for (int mt = blockIdx.x; mt < num_mtiles; mt += gridDim.x) {
                 KCursor c = cursor_at(kb_begin);
+                const TileOrg torg = tile_origin(mt);
+                int armed_left = mt == (int)blockIdx.x ? early : 0;   // k-blocks of this tile whose constant operand is already in flight
                 for (int kb = kb_begin; kb < kb_end; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
 #ifdef B2_BOUND_STUDY
@@ -261,10 +271,11 @@ __global__ void __launch_bounds__(IG_THREADS, IG_THREADS <= 192 ? 2 : 1) igemm_k
                         continue;
                     }
 #endif
-                    const bool armed = early > 0 && mt == (int)blockIdx.x && kb - kb_begin < early;   // requested before the PDL wait
+                    const bool armed = armed_left > 0;   // requested before the PDL wait
+                    armed_left -= armed;
                     if (!armed) mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
-                    if (!(armed && (p.epi.flags & IG_CONST_A))) load_src(stage, c, mt);
-                    if (!(armed && (p.epi.flags & IG_CONST_B))) load_w(stage, kb);
+                    if (!(armed && early_a)) load_src(stage, c, torg);
+                    if (!(armed && early_b)) load_w(stage, kb);
                     B2_TS(if (ts && mt == (int)blockIdx.x && kb == kb_begin) ts[2] = globaltimer_ns();)
                     cursor_next(c);
                     if (++stage == p.num_stages) {

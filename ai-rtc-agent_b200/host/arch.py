@@ -34,7 +34,7 @@ TINY_TURBO = UNetArch("tiny-turbo", (64, 128, 256, 256), (1, 2, 4, 4), 128, True
 
 
 def arch_for(model_id: str) -> UNetArch:
-    if model_id.startswith("tiny"):
+    if model_id.rstrip("/").rsplit("/", 1)[-1].startswith("tiny"):   # a model id or a local directory name
         return TINY_TURBO if "turbo" in model_id else TINY_SD15
     return SD_TURBO if "turbo" in model_id else SD15
 

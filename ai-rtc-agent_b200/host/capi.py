@@ -104,6 +104,8 @@ def lib() -> C.CDLL:
         _lib.b2sd_destroy.argtypes = [vp]
         _lib.b2sd_load_tensor.argtypes = [vp, C.c_char_p, vp, ci, C.POINTER(i64), ci]
         _lib.b2sd_prepare.argtypes = [vp, vp, vp, vp, vp, vp]
+        _lib.b2sd_export_packed.argtypes = [vp, C.c_char_p]
+        _lib.b2sd_import_packed.argtypes = [vp, C.c_char_p]
         _lib.b2sd_set_prompt_embeds.argtypes = [vp, vp, vp]
         _lib.b2sd_set_timesteps.argtypes = [vp, vp, vp]
         _lib.b2sd_step.argtypes = [vp, vp, ci, ci, vp, vp]
@@ -114,7 +116,7 @@ def lib() -> C.CDLL:
         _lib.b2sd_profile.restype = C.c_int
         _lib.b2sd_profile_kind.argtypes = [vp, C.c_char_p, ci, C.POINTER(C.c_double), C.POINTER(ci), C.POINTER(C.c_double), vp]
         _lib.b2sd_profile_kind.restype = C.c_int
-        for name in ("create", "destroy", "load_tensor", "prepare", "set_prompt_embeds", "set_timesteps", "step",
+        for name in ("create", "destroy", "load_tensor", "prepare", "export_packed", "import_packed", "set_prompt_embeds", "set_timesteps", "step",
                      "step_ex", "get_tensor", "launches_per_step"):
             getattr(_lib, "b2sd_" + name).restype = C.c_int
         for name in ("attention", "groupnorm", "layernorm", "upsample2x", "smallconv", "lcm_step", "post_u8"):

@@ -8,6 +8,7 @@ frame_buffer_size=1, cfg_type "self"/"none" with guidance_scale <= 1.0 (no CFG a
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Callable, Dict, List, Optional
 
 import numpy as np
@@ -72,7 +73,8 @@ class StreamDiffusion:
                  t_index_list: List[int], prompt_encoder: Callable[[str], torch.Tensor],
                  torch_dtype: torch.dtype = torch.float16, width: int = 512, height: int = 512,
                  do_add_noise: bool = True, use_denoising_batch: bool = True, frame_buffer_size: int = 1,
-                 cfg_type: str = "self", device: str = "cuda", use_cuda_graph: bool = True):
+                 cfg_type: str = "self", device: str = "cuda", use_cuda_graph: bool = True,
+                 packed_blob: Optional[str] = None):
         if frame_buffer_size != 1:
             raise NotImplementedError("frame_buffer_size > 1 is not on the reference's path (lib/pipeline.py:28)")
         if not use_denoising_batch:
@@ -124,8 +126,19 @@ class StreamDiffusion:
             self.device = torch.device("cuda", torch.cuda.current_device())
         torch.cuda.set_device(self.device)
         capi.check(self._lib.b2sd_create(C.byref(cfg), C.byref(self._handle)), "b2sd_create")
-        self._load("", unet_sd)
-        self._load("vae.", vae_sd)
+        if packed_blob is not None:
+            # kernel-native weights written by export_packed() / `python -m ai_rtc_agent_b200.pack`: no state dicts, no repacking
+            capi.check(self._lib.b2sd_import_packed(self._handle, os.fsencode(packed_blob)), f"b2sd_import_packed({packed_blob})")
+        else:
+            self._load("", unet_sd)
+            self._load("vae.", vae_sd)
+
+    def export_packed(self, path: str) -> None:
+        """Write the packed-weight blob (after prepare()); the engine-file cache of lib/wrapper.py:593-597, 896-910."""
+        self._check()
+        tmp = f"{path}.tmp{os.getpid()}"
+        capi.check(self._lib.b2sd_export_packed(self._handle, os.fsencode(tmp)), f"b2sd_export_packed({path})")
+        os.replace(tmp, path)   # atomic: a concurrently starting replica never sees a half-written blob
 
     def __del__(self):
         try:

@@ -106,6 +106,25 @@ def fuse_lora(unet_sd: Dict[str, torch.Tensor], lora_sd: Dict[str, torch.Tensor]
     return fused
 
 
+def packed_blob_path(engine_dir, model_id_or_path: str, arch_name: str, use_lcm_lora: bool, lcm_lora_id: Optional[str],
+                     lora_dict: Optional[Dict[str, float]], vae_id: Optional[str], synthetic: bool) -> str:
+    """Where the packed-weight blob of this model lives: `<engine_dir>/engines--<model>/b2sd-<arch>-<recipe hash>.b2pack`,
+    the directory naming of the reference's TensorRT cache (lib/wrapper.py:593, `engines--` + model id with / -> --).
+    The hash covers everything that changes the weight VALUES (LoRAs and their scales, LCM-LoRA, VAE, synthetic seed), not
+    batch / resolution / prompt (the blob does not depend on them, unlike the reference's static-shape engines)."""
+    import hashlib
+    import json
+    recipe = {"lcm": bool(use_lcm_lora), "lcm_id": lcm_lora_id, "vae": vae_id, "synthetic": bool(synthetic),
+              "loras": sorted((str(k), float(v)) for k, v in (lora_dict or {}).items())}
+    for path, _ in recipe["loras"]:
+        if os.path.exists(path):   # a replaced LoRA file must not hit the old blob
+            st = os.stat(path)
+            recipe.setdefault("lora_files", []).append((path, st.st_size, int(st.st_mtime)))
+    digest = hashlib.sha256(json.dumps(recipe, sort_keys=True).encode()).hexdigest()[:16]
+    name = "engines--" + model_id_or_path.strip("/").replace("/", "--")
+    return os.path.join(str(engine_dir), name, f"b2sd-{arch_name}-{digest}.b2pack")
+
+
 def resolve_weights(model_id_or_path: str, vae_id: Optional[str], lcm_lora_id: Optional[str], use_lcm_lora: bool,
                     lora_dict: Optional[Dict[str, float]], sd_turbo: bool
                     ) -> Tuple[A.UNetArch, Dict[str, torch.Tensor], Dict[str, torch.Tensor], Optional[str]]:

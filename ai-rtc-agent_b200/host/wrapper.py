@@ -120,6 +120,9 @@ class StreamDiffusionWrapper:
         self.batch_size = len(t_index_list) * frame_buffer_size if use_denoising_batch else frame_buffer_size
         self.use_denoising_batch = use_denoising_batch
         self.use_safety_checker = use_safety_checker
+        self.engine_dir = engine_dir
+        self.packed_blob = None
+        self._blob_to_write = None
         self.cuda_stream = CudaStreamPtr(cuda_stream_handle) if cuda_stream_handle is not None else None
         self._ext_stream = (torch.cuda.ExternalStream(cuda_stream_handle) if cuda_stream_handle is not None else None)
 
@@ -130,16 +133,40 @@ class StreamDiffusionWrapper:
     # -- model loading: replaces _load_trt_model/_load_model (lib/wrapper.py:409-944) --------------------
     def _load_model(self, model_id_or_path, lora_dict, lcm_lora_id, vae_id, t_index_list, do_add_noise,
                     use_lcm_lora, cfg_type) -> StreamDiffusion:
+        """Like the reference (lib/wrapper.py:583-615): first try the cached artefact under `engine_dir` -- there TensorRT engine
+        files, here the packed-weight blob -- and on any failure fall through to the full path (load weights, fuse LoRAs),
+        after which the blob is written for the next start (lib/wrapper.py:889-910 moves the engines into the cache)."""
+        import os
+        from . import arch as A
+        from . import weights as W
+        synthetic_ok = bool(os.getenv(W.ALLOW_SYNTHETIC_ENV)) or model_id_or_path.startswith(("tiny", "synthetic"))
+        repo = W.find_local_repo(model_id_or_path)
+        have_ckpt = repo is not None and os.path.isdir(os.path.join(repo, "unet"))
+        arch = A.arch_for(model_id_or_path)
+        kw = dict(torch_dtype=self.dtype, width=self.width, height=self.height, do_add_noise=do_add_noise,
+                  use_denoising_batch=self.use_denoising_batch, frame_buffer_size=self.frame_buffer_size, cfg_type=cfg_type,
+                  device=self.device)
+        blob = None
+        # blobs are kept for real checkpoints; seeded synthetic weights (benchmarks, tests) only with B200SD_PACK_CACHE=synthetic
+        mode = os.getenv("B200SD_PACK_CACHE", "1")
+        use_cache = self.engine_dir is not None and mode != "0" and model_id_or_path not in W._PRELOADED and \
+            (have_ckpt or mode == "synthetic")
+        if use_cache:
+            blob = W.packed_blob_path(self.engine_dir, model_id_or_path, arch.name, use_lcm_lora and not self.sd_turbo, lcm_lora_id,
+                                      lora_dict, vae_id, synthetic=not have_ckpt)
+        encoder = make_prompt_encoder(repo if have_ckpt else None, arch.cross_attention_dim, self.device, allow_synthetic=synthetic_ok)
+        if blob is not None and os.path.exists(blob) and (have_ckpt or synthetic_ok):
+            try:
+                sd = StreamDiffusion(arch, {}, {}, t_index_list, encoder, packed_blob=blob, **kw)
+                logger.info("loaded packed weights from %s", blob)
+                self.packed_blob = blob
+                return sd
+            except Exception as exc:   # noqa: BLE001 - same policy as lib/wrapper.py:611-615
+                logger.warning("packed-weight blob %s unusable (%s); rebuilding from the checkpoint", blob, exc)
         arch, unet_sd, vae_sd, repo = resolve_weights(model_id_or_path, vae_id, lcm_lora_id, use_lcm_lora, lora_dict,
                                                       self.sd_turbo)
-        import os
-        from .weights import ALLOW_SYNTHETIC_ENV
-        encoder = make_prompt_encoder(repo, arch.cross_attention_dim, self.device,
-                                      allow_synthetic=bool(os.getenv(ALLOW_SYNTHETIC_ENV)) or model_id_or_path.startswith(("tiny", "synthetic")))
-        return StreamDiffusion(arch, unet_sd, vae_sd, t_index_list, encoder, torch_dtype=self.dtype, width=self.width,
-                               height=self.height, do_add_noise=do_add_noise,
-                               use_denoising_batch=self.use_denoising_batch, frame_buffer_size=self.frame_buffer_size,
-                               cfg_type=cfg_type, device=self.device)
+        self._blob_to_write = blob
+        return StreamDiffusion(arch, unet_sd, vae_sd, t_index_list, encoder, **kw)
 
     def _on_stream(self):
         return torch.cuda.stream(self._ext_stream) if self._ext_stream is not None else _NullCtx()
@@ -154,6 +181,18 @@ class StreamDiffusionWrapper:
         with self._on_stream():
             self.stream.prepare(prompt, negative_prompt, num_inference_steps=num_inference_steps,
                                 guidance_scale=guidance_scale, delta=delta)
+        if self._blob_to_write is not None:
+            # first start from a checkpoint: leave the packed blob behind (the reference moves its freshly built engines into
+            # the cache directory, lib/wrapper.py:889-910); failures only cost the next start its speed-up
+            import os
+            try:
+                os.makedirs(os.path.dirname(self._blob_to_write), exist_ok=True)
+                self.stream.export_packed(self._blob_to_write)
+                self.packed_blob = self._blob_to_write
+                logger.info("wrote packed weights to %s", self._blob_to_write)
+            except Exception as exc:   # noqa: BLE001
+                logger.warning("could not write the packed-weight blob %s: %s", self._blob_to_write, exc)
+            self._blob_to_write = None
 
     def __call__(self, image=None, prompt: Optional[str] = None, t_index_list: Optional[List[int]] = None):
         if self.mode == "img2img":

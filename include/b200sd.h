@@ -153,8 +153,19 @@ int b2sd_destroy(b2sd_handle h);
 
 /* Weights under diffusers state-dict names: UNet keys as-is ("down_blocks.0.resnets.0.conv1.weight"),
  * TAESD keys prefixed "vae." ("vae.encoder.layers.0.weight").  ptr may be host or device memory.
- * dtype: 0 = fp16, 1 = fp32.  Replaces the ONNX export + TensorRT build of lib/wrapper.py:785-910. */
+ * dtype: 0 = fp16, 1 = fp32.  Replaces the ONNX export + TensorRT build of lib/wrapper.py:785-910.
+ * After the first b2sd_prepare the raw copies of parameters that only feed the packing kernels are released (set
+ * B2_KEEP_RAW=1 to keep them); loading further tensors into such an engine is an error. */
 int b2sd_load_tensor(b2sd_handle h, const char* key, const void* ptr, int dtype, const int64_t* shape, int ndim);
+
+/* Packed-weight blob: the kernel-native layouts b2sd_prepare derives from the parameters (reordered convolution
+ * matrices, per-head q/k/v gathers, GEGLU interleave, fused bias vectors), written once and loaded instead of
+ * b2sd_load_tensor + repacking.  Replaces the reference's cached TensorRT engine files `engines--<model>/...engine`
+ * (lib/wrapper.py:593-597, 896-910; build.py:11-32).  The blob depends on the architecture and the (LoRA-fused)
+ * parameter values only -- not on batch, image size or prompt.  Export after b2sd_prepare; import into a fresh engine
+ * (same b2sd_config architecture fields) before b2sd_prepare.  Host synchronous. */
+int b2sd_export_packed(b2sd_handle h, const char* path);
+int b2sd_import_packed(b2sd_handle h, const char* path);
 
 /* StreamDiffusion.prepare (via lib/wrapper.py:197-234): fixes per-slot scalars and noise, zeroes the
  * stream-batch latent buffer, builds the frame program.  All pointers are HOST memory:

@@ -184,3 +184,101 @@ def test_weight_broadcast_world_size_2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res[0][1] == res[1][1] and res[0][2] == res[1][2] > 50
+
+
+def _write_tiny_checkpoint(root, with_lora=True):
+    """A diffusers-layout checkpoint tree on disk (the files download.py:17-25 would fetch), tiny-width: unet/, TAESD repo,
+    an LCM-LoRA in peft naming and a style LoRA in kohya naming."""
+    import torch
+    from safetensors.torch import save_file
+    from ai_rtc_agent_b200.host import arch as A
+    arch = A.TINY_SD15
+    unet = A.synthetic_state_dict(A.unet_param_shapes(arch), seed=5)
+    vae = A.synthetic_state_dict(A.taesd_param_shapes(), seed=6, relu_net=True)
+    model_dir = os.path.join(root, "tiny-sd15-ckpt")
+    os.makedirs(os.path.join(model_dir, "unet"))
+    save_file({k: v.contiguous() for k, v in unet.items()}, os.path.join(model_dir, "unet", "diffusion_pytorch_model.fp16.safetensors"))
+    taesd_dir = os.path.join(root, "taesd")
+    os.makedirs(taesd_dir)
+    save_file({k: v.contiguous() for k, v in vae.items()}, os.path.join(taesd_dir, "diffusion_pytorch_model.safetensors"))
+    g = torch.Generator().manual_seed(9)
+    tq = "down_blocks.0.attentions.0.transformer_blocks.0.attn1.to_q"
+    ff = "mid_block.attentions.0.transformer_blocks.0.ff.net.2"
+    lcm = {f"unet.{tq}.lora_A.weight": torch.randn(4, 64, generator=g).half(), f"unet.{tq}.lora_B.weight": torch.randn(64, 4, generator=g).half(),
+           f"unet.{ff}.lora_A.weight": torch.randn(4, 1024, generator=g).half(), f"unet.{ff}.lora_B.weight": torch.randn(256, 4, generator=g).half()}
+    lcm_dir = os.path.join(root, "lcm-lora")
+    os.makedirs(lcm_dir)
+    save_file(lcm, os.path.join(lcm_dir, "pytorch_lora_weights.safetensors"))
+    kohya = "lora_unet_" + "up_blocks.3.resnets.0.conv1".replace(".", "_")
+    style = {kohya + ".lora_down.weight": torch.randn(2, 192, 3, 3, generator=g).half(), kohya + ".lora_up.weight": torch.randn(64, 2, 1, 1, generator=g).half(),
+             kohya + ".alpha": torch.tensor(1.0)}
+    style_path = os.path.join(root, "style.safetensors")
+    save_file(style, style_path)
+    return model_dir, taesd_dir, lcm_dir, style_path, unet, vae, lcm, style
+
+
+def test_checkpoint_on_disk_lora_fusing_end_to_end(tmp_path):
+    """load_unet / load_taesd / fuse_lora (lib/wrapper.py:645-707) on a real directory tree: peft (`lora_A/B`) and kohya
+    (`lora_unet_*`, alpha) key styles must land on the right parameters, with W += scale * alpha/rank * up @ down."""
+    import torch
+    from ai_rtc_agent_b200.host import weights as W
+    model_dir, taesd_dir, lcm_dir, style_path, unet, vae, lcm, style = _write_tiny_checkpoint(str(tmp_path))
+    arch, usd, vsd, repo = W.resolve_weights(model_dir, taesd_dir, lcm_dir, True, {style_path: 0.5}, sd_turbo=False)
+    assert repo == model_dir and arch.name in ("sd15", "tiny-sd15")
+    assert set(usd) == set(unet) and set(vsd) == set(vae)
+    tq = "down_blocks.0.attentions.0.transformer_blocks.0.attn1.to_q.weight"
+    want = unet[tq].float() + lcm["unet." + tq[:-7] + ".lora_B.weight"].float() @ lcm["unet." + tq[:-7] + ".lora_A.weight"].float()
+    assert torch.allclose(usd[tq].float(), want.half().float(), atol=2e-3)
+    ck = "up_blocks.3.resnets.0.conv1.weight"
+    kohya = "lora_unet_" + ck[:-7].replace(".", "_")
+    delta = (style[kohya + ".lora_up.weight"].float().flatten(1) @ style[kohya + ".lora_down.weight"].float().flatten(1)) * (0.5 * 1.0 / 2)
+    assert torch.allclose(usd[ck].float(), (unet[ck].float() + delta.reshape(unet[ck].shape)).half().float(), atol=2e-3)
+    untouched = "conv_in.weight"
+    assert torch.equal(usd[untouched], unet[untouched])
+
+
+def test_lora_that_does_not_apply_is_an_error(tmp_path):
+    """A LoRA whose module names match nothing must not be skipped silently (an un-fused LCM-LoRA leaves SD-1.5
+    un-distilled while it is run at 4 steps)."""
+    import torch
+    from ai_rtc_agent_b200.host.weights import fuse_lora
+    sd = {"mid_block.resnets.0.conv1.weight": torch.zeros(8, 8, 3, 3, dtype=torch.float16)}
+    bad = {"unet.some.other.module.lora_A.weight": torch.zeros(2, 8), "unet.some.other.module.lora_B.weight": torch.zeros(8, 2)}
+    with pytest.raises(KeyError, match="matched 0 of 1"):
+        fuse_lora(sd, bad)
+    assert fuse_lora(sd, bad, strict=False) == 0
+    te_only = {"lora_te_text_model_encoder_layers_0_mlp_fc1.lora_down.weight": torch.zeros(2, 8),
+               "lora_te_text_model_encoder_layers_0_mlp_fc1.lora_up.weight": torch.zeros(8, 2)}
+    with pytest.raises(KeyError):      # nothing for the UNet at all
+        fuse_lora(sd, te_only)
+
+
+def test_real_checkpoint_needs_its_text_encoder(tmp_path):
+    """make_prompt_encoder: a checkpoint directory without a loadable text_encoder/ is an error, never a silent fallback
+    to hash-seeded embeddings."""
+    from ai_rtc_agent_b200.host.prompt import SyntheticPromptEncoder, make_prompt_encoder
+    d = tmp_path / "ckpt"
+    d.mkdir()
+    with pytest.raises(FileNotFoundError):
+        make_prompt_encoder(str(d), 768, "cpu")
+    (d / "text_encoder").mkdir()
+    with pytest.raises(Exception):     # present but not loadable
+        make_prompt_encoder(str(d), 768, "cpu")
+    assert isinstance(make_prompt_encoder(None, 768, "cpu"), SyntheticPromptEncoder)
+    assert isinstance(make_prompt_encoder(str(tmp_path / "nope"), 768, "cpu", allow_synthetic=True), SyntheticPromptEncoder)
+
+
+def test_packed_blob_path_follows_the_reference_cache_naming():
+    from ai_rtc_agent_b200.host import weights as W
+    a = W.packed_blob_path("./models/engines", "lykon/dreamshaper-8", "sd15", True, None, {"ghibli.safetensors": 1.0}, None, False)
+    b = W.packed_blob_path("./models/engines", "lykon/dreamshaper-8", "sd15", True, None, {"ghibli.safetensors": 0.8}, None, False)
+    c = W.packed_blob_path("./models/engines", "lykon/dreamshaper-8", "sd15", True, None, None, None, False)
+    assert os.path.dirname(a) == os.path.join("./models/engines", "engines--lykon--dreamshaper-8")   # lib/wrapper.py:593
+    assert a.endswith(".b2pack") and len({a, b, c}) == 3, "the LoRA recipe is part of the key"
+
+
+def test_pack_cli_argument_parsing():
+    from ai_rtc_agent_b200 import pack
+    assert pack.parse_lora(["a.safetensors:0.5", "/x/y.safetensors"]) == {"a.safetensors": 0.5, "/x/y.safetensors": 1.0}
+    with pytest.raises(SystemExit):
+        pack.parse_lora(["a.safetensors:fast"])

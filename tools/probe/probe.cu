@@ -8,7 +8,7 @@
 #include <cudaTypedefs.h>
 #include <stdlib.h>
 
-#include "../../include/b200sd.h"
+#include "../../include/b200sd.h"  // C-ABI conventions only
 #include "igemm.cuh"
 #include "ptx.cuh"
 
@@ -202,7 +202,7 @@ extern "C" int b2sd_probe_umma_rowshift(const void* A, int rows_a, const void* B
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ||
         enc(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(B), db, st, bb, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
-        b2_set_error("probe: tensor map encode failed");
+        fprintf(stderr, "probe: tensor map encode failed\n");
         return -1;
     }
     p.D = static_cast<float*>(D);

@@ -1,8 +1,8 @@
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from ai_rtc_agent_b200.host import capi
-lib = capi.lib()
+PROBE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "probe", "libb200probe.so")  # make -C tools/probe
+lib = C.CDLL(PROBE)
 lib.b2sd_probe_umma_rowshift.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
