@@ -44,8 +44,16 @@ static void to_igemm_desc(const b2sd_igemm_desc* d, IgemmDesc& g) {
     g.epi.ldr = d->ldr;
     g.epi.acc_scale = d->acc_scale;
     g.epi.res_scale = d->res_scale;
-    g.epi.flags = d->flags & (IG_RELU | IG_GEGLU | IG_CONST_A | IG_CONST_B);
+    g.epi.flags = d->flags & (IG_RELU | IG_GEGLU);
     g.epi.n_valid = d->n_valid;
+    g.epi.rowstat_out = static_cast<unsigned long long*>(d->rowstat_out);
+    g.epi.rowstat_in = static_cast<const unsigned long long*>(d->rowstat_in);
+    g.epi.colsum = d->colsum;
+    g.epi.ln_inv_c = d->ln_c > 0 ? 1.f / (float)d->ln_c : 0.f;
+    g.epi.ln_eps = d->ln_eps;
+    g.epi.out2 = reinterpret_cast<__half*>(d->out2);
+    g.epi.ld2 = d->ld2;
+    g.epi.col2 = d->col2;
 }
 
 int b2sd_op_igemm(const b2sd_igemm_desc* d, void* stream) {

@@ -974,4 +974,43 @@ int gather_rows_launch(const __half* src, int src_ld, const int* perm, __half* d
     return 0;
 }
 
+// ---- LayerNorm folded into the consumer GEMM (load-time preparation; one warp per weight row) -----------------------
+__global__ void scale_cols_kernel(__half* w, long rows, int k, const float* __restrict__ g) {
+    const long r = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    for (int c = threadIdx.x & 31; c < k; c += 32) w[r * k + c] = __float2half_rn(__half2float(w[r * k + c]) * g[c]);
+}
+__global__ void row_sum_kernel(const __half* __restrict__ w, long rows, int k, float* out) {
+    const long r = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    float a = 0.f;
+    for (int c = threadIdx.x & 31; c < k; c += 32) a += __half2float(w[r * k + c]);
+    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) out[r] = a;
+}
+__global__ void row_dot_kernel(const __half* __restrict__ w, long rows, int k, const float* __restrict__ v,
+                               const float* __restrict__ bias, float* out) {
+    const long r = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    float a = 0.f;
+    for (int c = threadIdx.x & 31; c < k; c += 32) a += __half2float(w[r * k + c]) * v[c];
+    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) out[r] = a + (bias ? bias[r] : 0.f);
+}
+int scale_cols_launch(__half* w, long rows, int k, const float* gamma, cudaStream_t s) {
+    scale_cols_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(w, rows, k, gamma);
+    B2_CHECK_LAUNCH("scale_cols");
+    return 0;
+}
+int row_sum_launch(const __half* w, long rows, int k, float* out, cudaStream_t s) {
+    row_sum_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(w, rows, k, out);
+    B2_CHECK_LAUNCH("row_sum");
+    return 0;
+}
+int row_dot_launch(const __half* w, long rows, int k, const float* v, const float* bias, float* out, cudaStream_t s) {
+    row_dot_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(w, rows, k, v, bias, out);
+    B2_CHECK_LAUNCH("row_dot");
+    return 0;
+}
+
 }  // namespace b2

@@ -80,4 +80,10 @@ int pack_conv_weight_launch(const __half* w_oihw, __half* dst, int dst_ld, int k
 int gather_rows_launch(const __half* src, int src_ld, const int* perm, __half* dst, int dst_ld, int rows, int cols,
                        cudaStream_t s);
 
+// LayerNorm folded into its consumer GEMM, load-time preparation on packed [rows][k] fp16 weights:
+//   scale_cols: W'[n][k] = W[n][k] * gamma[k];  row_sum: s[n] = sum_k W'[n][k];  row_dot: b'[n] = sum_k W[n][k] * beta[k] (+ bias[n])
+int scale_cols_launch(__half* w, long rows, int k, const float* gamma, cudaStream_t s);
+int row_sum_launch(const __half* w, long rows, int k, float* out, cudaStream_t s);
+int row_dot_launch(const __half* w, long rows, int k, const float* v, const float* bias, float* out, cudaStream_t s);
+
 }  // namespace b2

@@ -11,7 +11,6 @@
 
 #include <functional>
 #include <map>
-#include <memory>
 #include <string>
 #include <vector>
 
@@ -103,9 +102,6 @@ struct Op {
     std::function<int(cudaStream_t)> fn;
     std::string name;
     double flops = 0.0;  // algorithmic 2*MAC count of the launch (0 for non-contraction kernels)
-    std::shared_ptr<IgemmPlan> ig;   // contraction launches: the plan the closure launches (patched after the build: L2 prefetch chain)
-    const void* wptr = nullptr;      // its constant (weight) operand, for the predecessor's L2 prefetch
-    size_t wbytes = 0;
     template <class F>
     Op(F f, std::string n = "", double fl = 0.0) : fn(std::move(f)), name(std::move(n)), flops(fl) {}
     int operator()(cudaStream_t s) const { return fn(s); }
@@ -148,7 +144,8 @@ int igemm_autotile(IgemmDesc d, bool allow_swap, IgemmPlan* plan_out) {
         return 0;
     }
     d.swap = 0;
-    if (tuned && !geglu && n_gemm % 160 == 0 && total_kb >= 40) {
+    auto vt_ok = [&](int bn) { return !d.epi.out2 || d.epi.col2 % bn == 0; };   // fused q/k/v: an N tile is all q/k or all v
+    if (tuned && !geglu && n_gemm % 160 == 0 && total_kb >= 40 && vt_ok(160)) {
         // K-heavy contractions that cannot fill the GPU with 160-wide tiles alone (batch 1): wide tiles + cluster
         // split-K beat 64-wide tiles (profiles/r01_tile_sweep.md: -10..-40 % per launch, weights streamed from HBM)
         d.BN = 160; d.splits = 1; d.partial = nullptr;
@@ -158,7 +155,7 @@ int igemm_autotile(IgemmDesc d, bool allow_swap, IgemmPlan* plan_out) {
         int bn = 0, splits = 0;
         if (tiles < 132) {
             if (m_tiles >= 8) { bn = 160; splits = 4; }
-            else if (m_tiles >= 2 && n_gemm % 256 == 0 && total_kb >= 180) { bn = 256; splits = 8; }
+            else if (m_tiles >= 2 && n_gemm % 256 == 0 && total_kb >= 180 && vt_ok(256)) { bn = 256; splits = 8; }
         }
         if (bn) {
             d.BN = bn; d.splits = splits;
@@ -170,7 +167,7 @@ int igemm_autotile(IgemmDesc d, bool allow_swap, IgemmPlan* plan_out) {
     std::vector<int> valid;
     for (int bn : cands) {
         if (geglu && (bn % 32 != 0 || bn < 64)) continue;
-        if (n_gemm % bn == 0) valid.push_back(bn);
+        if (n_gemm % bn == 0 && vt_ok(bn)) valid.push_back(bn);
     }
     if (valid.empty()) {  // ragged N: one masked tile size
         int bn = 16;
@@ -230,6 +227,8 @@ struct b2sd_engine {
     int* tile_counters = nullptr;
     float coef_host[4][64]{};
 
+    unsigned long long* ln_stats = nullptr;   // slab of per-row LayerNorm statistics [rows][2] (see IgEpilogue::rowstat_out)
+    size_t ln_stats_cap = 0, ln_stats_used = 0;   // in 64-bit words
     std::vector<Op> prog_frame, prog_prompt, prog_time;
     std::map<std::string, Act> taps;
     SmallConvArgs head{};   // encoder head (reads the caller's frame)
@@ -355,6 +354,45 @@ struct b2sd_engine {
         return dst;
     }
 
+    // LayerNorm folded into a consumer GEMM (IgEpilogue::colsum): W' = gather(parts) diag(gamma) in place of the gathered rows,
+    // colsum[n] = sum_k W'[n][k], bias'[n] = sum_k W[n][k] beta[k] + bias[n].  Cached like every packed parameter.
+    struct LnFold { __half* w = nullptr; const float* colsum = nullptr; const float* bias = nullptr; };
+    int fold_ln(const std::string& name, const std::vector<std::pair<std::string, std::vector<int>>>& parts, int K,
+                const std::string& ln_prefix, const float* bias_vec, LnFold* out, cudaStream_t s) {
+        size_t rows = 0;
+        for (auto& p : parts) rows += p.second.size();
+        const size_t rows_pad = (rows + 15) / 16 * 16;
+        const bool done = packed.count(name) && fvec.count(name + ":cs") && fvec.count(name + ":b");
+        __half* w = pack_rows(name, parts, K, s);
+        if (!w) return -1;
+        if (!done) {
+            const float* gamma = vec({ln_prefix + ".weight"});
+            const float* beta = vec({ln_prefix + ".bias"});
+            float* cs = static_cast<float*>(weights.alloc(rows_pad * sizeof(float)));
+            float* bb = static_cast<float*>(weights.alloc(rows_pad * sizeof(float)));
+            if (!gamma || !beta || !cs || !bb) return -1;
+            cudaMemsetAsync(bb, 0, rows_pad * sizeof(float), s);
+            TRY(row_dot_launch(w, (long)rows, K, beta, bias_vec, bb, s));     // on the un-scaled rows
+            TRY(scale_cols_launch(w, (long)rows_pad, K, gamma, s));
+            TRY(row_sum_launch(w, (long)rows_pad, K, cs, s));
+            fvec[name + ":cs"] = cs; fvec_bytes[name + ":cs"] = rows_pad * sizeof(float);
+            fvec[name + ":b"] = bb; fvec_bytes[name + ":b"] = rows_pad * sizeof(float);
+        }
+        out->w = w;
+        out->colsum = fvec[name + ":cs"];
+        out->bias = fvec[name + ":b"];
+        return 0;
+    }
+    unsigned long long* alloc_rowstat(long rows) {
+        if (ln_stats_used + 2 * (size_t)rows > ln_stats_cap) {
+            b2_set_error("LayerNorm statistics slab exhausted");
+            return nullptr;
+        }
+        unsigned long long* p = ln_stats + ln_stats_used;
+        ln_stats_used += 2 * (size_t)rows;
+        return p;
+    }
+
     // ---- program construction helpers -----------------------------------------------------------
     Act new_act(int n, int h, int w, int c, int ld = 0) {
         Act a;
@@ -366,57 +404,29 @@ struct b2sd_engine {
     static ActView tokens(const Act& a) { return ActView{a.p, 1, 1, a.n * a.h * a.w, a.c, a.ld}; }
 
     // choose N tile / split-K for a good grid (igemm_autotile), plan, and append the launch
-    // append a planned contraction; remembers its constant operand so the previous contraction can prefetch it into L2
-    void push_igemm(std::vector<Op>& dst, const IgemmPlan& plan, const IgemmDesc& d, const std::string& label, double flops) {
-        auto sp = std::make_shared<IgemmPlan>(plan);
-        Op op([sp](cudaStream_t s) { return igemm_launch(*sp, s); }, label, flops);
-        op.ig = sp;
-        if (d.epi.flags & IG_CONST_A) {
-            op.wptr = d.src[0].ptr;
-            op.wbytes = (size_t)d.src[0].N * d.src[0].H * d.src[0].W * d.src[0].ld * 2;
-        } else if (d.epi.flags & IG_CONST_B) {
-            op.wptr = d.w;
-            op.wbytes = (size_t)d.w_rows * d.w_ld * 2;
-        }
+    // append a planned contraction
+    void push_igemm(std::vector<Op>& dst, const IgemmPlan& plan, const std::string& label, double flops) {
         if (&dst == &prog_frame) launches += 1;
-        dst.push_back(std::move(op));
+        dst.push_back(Op([plan](cudaStream_t s) { return igemm_launch(plan, s); }, label, flops));
     }
 
-    // choose N tile / split-K for a good grid (igemm_autotile), plan, and append the launch.  Every contraction of the
-    // engine has a packed weight matrix as its `w` operand unless the caller marked the activation view as the constant one.
+    // choose N tile / split-K for a good grid (igemm_autotile), plan, and append the launch
     int add_igemm(std::vector<Op>& dst, IgemmDesc d) {
-        static const bool no_early = getenv("B2_NO_EARLY") != nullptr;
-        if (no_early) d.epi.flags &= ~(IG_CONST_A | IG_CONST_B);
-        else if (!(d.epi.flags & IG_CONST_A)) d.epi.flags |= IG_CONST_B;
         const bool geglu = (d.epi.flags & IG_GEGLU) != 0;
         const int n_gemm = geglu ? 2 * d.epi.n_valid : d.epi.n_valid;
+        const bool extras = d.epi.rowstat_out || d.epi.colsum || d.epi.out2;   // not implemented by the swapped-orientation epilogue
         IgemmPlan plan;
-        TRY(igemm_autotile(d, allow_swap, &plan));
+        TRY(igemm_autotile(d, allow_swap && !extras, &plan));
+        if (d.epi.out2 && d.epi.col2 % plan.p.BN != 0) {   // an N tile must be all q/k or all v (igemm_autotile filters on it)
+            b2_set_error("fused q/k/v projection: N tile %d does not divide the V offset %d", plan.p.BN, d.epi.col2);
+            return -1;
+        }
         char label[256];
         snprintf(label, sizeof(label), "igemm %s rows=%ld n=%d kb=%d bn=%d splits=%d grid=%u,%u,%u %s", cur.c_str(),
                  plan.rows_total, d.epi.n_valid, plan.p.total_kb, plan.p.BN, plan.splits, plan.grid.x, plan.grid.y,
                  plan.grid.z, plan.p.swap ? "swapped" : "taps");
-        push_igemm(dst, plan, d, label, 2.0 * (double)plan.rows_total * n_gemm * plan.p.total_kb * IG_BK);
+        push_igemm(dst, plan, label, 2.0 * (double)plan.rows_total * n_gemm * plan.p.total_kb * IG_BK);
         return 0;
-    }
-
-    // Chain the L2 prefetch: contraction i pulls the weights of contraction i+1 (the last one those of the first: next frame).
-    void link_weight_prefetch(std::vector<Op>& ops) {
-        static const bool off = getenv("B2_NO_L2PF") != nullptr;
-        static const char* cap_env = getenv("B2_L2PF_MAX_MB");
-        const size_t cap = (size_t)(cap_env ? atoi(cap_env) : 64) << 20;
-        std::vector<Op*> ig;
-        for (auto& op : ops)
-            if (op.ig) ig.push_back(&op);
-        for (size_t i = 0; i < ig.size(); ++i) {
-            const Op* nxt = ig[(i + 1) % ig.size()];
-            IgemmPlan& pl = *ig[i]->ig;
-            pl.p.pf_ptr = nullptr;
-            pl.p.pf_bytes = 0;
-            if (off || !nxt->wptr || nxt->wbytes == 0 || nxt->wbytes > cap || pl.mode != 0) continue;
-            pl.p.pf_ptr = nxt->wptr;
-            pl.p.pf_bytes = nxt->wbytes & ~(size_t)15;
-        }
     }
 
     int add_groupnorm(const Act& xa, const Act* xb, const std::string& prefix, const Act& y, float eps, int silu) {
@@ -491,9 +501,26 @@ struct b2sd_engine {
     }
 
     // Linear over tokens: y = x W^T (+bias) (+res)
+    struct LinExtra {   // LayerNorm-fold / row-statistics / transposed-V options of a Linear (IgEpilogue)
+        unsigned long long* rowstat_out = nullptr;
+        const unsigned long long* rowstat_in = nullptr;
+        const float* colsum = nullptr;
+        int ln_c = 0;
+        __half* out2 = nullptr;
+        int ld2 = 0, col2 = 0;
+    };
     int add_linear(std::vector<Op>& dst, const ActView& x, const __half* w, int n, int k, const float* bias,
-                   __half* out, int ldc, const __half* res, int ldr, int flags = 0, int n_valid = -1) {
+                   __half* out, int ldc, const __half* res, int ldr, int flags = 0, int n_valid = -1,
+                   const LinExtra* ex = nullptr) {
         IgemmDesc d{};
+        if (ex) {
+            d.epi.rowstat_out = ex->rowstat_out;
+            d.epi.rowstat_in = ex->rowstat_in;
+            d.epi.colsum = ex->colsum;
+            d.epi.ln_inv_c = ex->ln_c ? 1.f / (float)ex->ln_c : 0.f;
+            d.epi.ln_eps = 1e-5f;
+            d.epi.out2 = ex->out2; d.epi.ld2 = ex->ld2; d.epi.col2 = ex->col2;
+        }
         d.nseg = 1; d.src[0] = x; d.ntap[0] = 1;
         d.w = w; d.w_rows = n; d.w_ld = k;
         d.stride = 1;
@@ -625,43 +652,76 @@ int b2sd_engine::build_transformer(const std::string& p, const Act& x, int heads
     };
     Act n = new_act(B, x.h, x.w, C);
     TRY(add_groupnorm(x, nullptr, p + "norm", n, 1e-6f, 0));
+    const int HWp = (HW + 7) / 8 * 8;
+    const bool one_gemm = (HW % 8 == 0) || B == 1;   // V^T of all batch items is one [Cp][B*HW] matrix (TMA needs 16-byte column origins)
+    // LayerNorm folding + fused q/k/v projection: norm1/2/3 never run as kernels.  Each LayerNorm input is produced by a Linear
+    // whose epilogue also accumulates the row statistics (rowstat_out); the consumer GEMM runs on the RAW rows with gamma folded
+    // into its weights and applies mean / rstd in its epilogue (IgEpilogue::colsum).  B2_NO_LNFOLD=1 restores the three
+    // layernorm launches + separate V^T GEMM (also used when the batch's V^T columns need per-image padding).
+    static const bool no_fold = getenv("B2_NO_LNFOLD") != nullptr;
+    const bool fold = !no_fold && one_gemm;
+    const int inner = 4 * C;
+    std::vector<int> gperm;   // GEGLU: weight rows interleaved per 128-wide tile as [64 value | 64 gate]
+    {
+        const int half = 64;
+        for (int tI = 0; tI < inner / half; ++tI) {
+            for (int i = 0; i < half; ++i) gperm.push_back(tI * half + i);
+            for (int i = 0; i < half; ++i) gperm.push_back(inner + tI * half + i);
+        }
+    }
+    const float* bff1 = vec({t + "ff.net.0.proj.bias"}, &gperm);
+    if (!bff1) return -1;
     // proj_in: Linear (SD-Turbo) or 1x1 conv (SD-1.5) -- the same GEMM on NHWC tokens
     const Raw* wpi = get(p + "proj_in.weight");
     if (!wpi) return -1;
     Act hs = new_act(B, x.h, x.w, C);
-    TRY(add_linear(prog_frame, tokens(n), wpi->p, C, C, vec({p + "proj_in.bias"}), hs.p, C, nullptr, 0));
+    unsigned long long *st1 = nullptr, *st2 = nullptr, *st3 = nullptr;
+    if (fold) {
+        st1 = alloc_rowstat(M); st2 = alloc_rowstat(M); st3 = alloc_rowstat(M);
+        if (!st1 || !st2 || !st3) return -1;
+    }
+    {
+        LinExtra ex; ex.rowstat_out = st1;
+        TRY(add_linear(prog_frame, tokens(n), wpi->p, C, C, vec({p + "proj_in.bias"}), hs.p, C, nullptr, 0, 0, -1, &ex));
+    }
     // ---- self attention
-    Act ln = new_act(B, x.h, x.w, C);
-    TRY(add_layernorm(hs, t + "norm1", ln));
-    __half* wqk = pack_rows(t + "attn1.qk", {{t + "attn1.to_q.weight", head_perm(0)}, {t + "attn1.to_k.weight", head_perm(0)}}, C, s);
-    __half* wv = pack_rows(t + "attn1.v", {{t + "attn1.to_v.weight", head_perm(0)}}, C, s);
-    if (!wqk || !wv) return -1;
     Act qk = new_act(1, 1, (int)M, 2 * Cp);
-    TRY(add_linear(prog_frame, tokens(ln), wqk, 2 * Cp, C, nullptr, qk.p, 2 * Cp, nullptr, 0));
-    // V^T = Wv . ln^T : weights on the M side, tokens on the N side.  TMA needs the per-batch column origin
-    // 16-byte aligned, so when HW is not a multiple of 8 each batch item gets its own padded column range.
-    const int HWp = (HW + 7) / 8 * 8;
-    const bool one_gemm = (HW % 8 == 0) || B == 1;
     const long vt_ld = one_gemm ? (M + 7) / 8 * 8 : (long)B * HWp;
     const long vt_bstride = one_gemm ? HW : HWp;
     __half* vt = static_cast<__half*>(prog.alloc((size_t)Cp * vt_ld * 2));
     if (!vt) return -1;
     cudaMemsetAsync(vt, 0, (size_t)Cp * vt_ld * 2, s);  // pad columns must stay finite (0 * NaN = NaN in P.V)
-    allow_swap = false;  // V^T already has the weights on the M side
-    for (int bi = 0; bi < (one_gemm ? 1 : B); ++bi) {
-        ActView wv_view{wv, 1, 1, Cp, C, C};
-        IgemmDesc d{};
-        d.nseg = 1; d.src[0] = wv_view; d.ntap[0] = 1;
-        d.w = one_gemm ? ln.p : ln.p + (long)bi * HW * ln.ld;
-        d.w_rows = one_gemm ? (int)M : HW; d.w_ld = C; d.stride = 1;
-        d.Nb = 1; d.Ho = 1; d.Wo = Cp;
-        d.epi.out = one_gemm ? vt : vt + (long)bi * HWp;
-        d.epi.ldc = (int)vt_ld; d.epi.acc_scale = 1.f; d.epi.res_scale = 1.f;
-        d.epi.n_valid = one_gemm ? (int)M : HW;
-        d.epi.flags = IG_CONST_A;   // the "activation view" is W_v; the `w` operand is the LayerNorm output of this frame
-        TRY(add_igemm(prog_frame, d));
+    if (fold) {
+        // one GEMM: [q | k | v] rows; q/k columns go to `qk`, the V block is stored transposed (K-major V^T for the P.V MMA)
+        LnFold f;
+        TRY(fold_ln(t + "attn1.qkv+ln", {{t + "attn1.to_q.weight", head_perm(0)}, {t + "attn1.to_k.weight", head_perm(0)},
+                                         {t + "attn1.to_v.weight", head_perm(0)}}, C, t + "norm1", nullptr, &f, s));
+        LinExtra ex; ex.rowstat_in = st1; ex.colsum = f.colsum; ex.ln_c = C; ex.out2 = vt; ex.ld2 = (int)vt_ld; ex.col2 = 2 * Cp;
+        TRY(add_linear(prog_frame, tokens(hs), f.w, 3 * Cp, C, f.bias, qk.p, 2 * Cp, nullptr, 0, 0, -1, &ex));
+    } else {
+        Act ln = new_act(B, x.h, x.w, C);
+        TRY(add_layernorm(hs, t + "norm1", ln));
+        __half* wqk = pack_rows(t + "attn1.qk", {{t + "attn1.to_q.weight", head_perm(0)}, {t + "attn1.to_k.weight", head_perm(0)}}, C, s);
+        __half* wv = pack_rows(t + "attn1.v", {{t + "attn1.to_v.weight", head_perm(0)}}, C, s);
+        if (!wqk || !wv) return -1;
+        TRY(add_linear(prog_frame, tokens(ln), wqk, 2 * Cp, C, nullptr, qk.p, 2 * Cp, nullptr, 0));
+        // V^T = Wv . ln^T : weights on the M side, tokens on the N side.  TMA needs the per-batch column origin
+        // 16-byte aligned, so when HW is not a multiple of 8 each batch item gets its own padded column range.
+        allow_swap = false;  // V^T already has the weights on the M side
+        for (int bi = 0; bi < (one_gemm ? 1 : B); ++bi) {
+            ActView wv_view{wv, 1, 1, Cp, C, C};
+            IgemmDesc d{};
+            d.nseg = 1; d.src[0] = wv_view; d.ntap[0] = 1;
+            d.w = one_gemm ? ln.p : ln.p + (long)bi * HW * ln.ld;
+            d.w_rows = one_gemm ? (int)M : HW; d.w_ld = C; d.stride = 1;
+            d.Nb = 1; d.Ho = 1; d.Wo = Cp;
+            d.epi.out = one_gemm ? vt : vt + (long)bi * HWp;
+            d.epi.ldc = (int)vt_ld; d.epi.acc_scale = 1.f; d.epi.res_scale = 1.f;
+            d.epi.n_valid = one_gemm ? (int)M : HW;
+            TRY(add_igemm(prog_frame, d));
+        }
+        allow_swap = true;
     }
-    allow_swap = true;
     Act ao = new_act(B, x.h, x.w, C);
     {
         AttnDesc a{};
@@ -679,14 +739,14 @@ int b2sd_engine::build_transformer(const std::string& p, const Act& x, int heads
     const Raw* wo1 = get(t + "attn1.to_out.0.weight");
     if (!wo1) return -1;
     Act hs2 = new_act(B, x.h, x.w, C);
-    TRY(add_linear(prog_frame, tokens(ao), wo1->p, C, C, vec({t + "attn1.to_out.0.bias"}), hs2.p, C, hs.p, C));
+    {
+        LinExtra ex; ex.rowstat_out = st2;
+        TRY(add_linear(prog_frame, tokens(ao), wo1->p, C, C, vec({t + "attn1.to_out.0.bias"}), hs2.p, C, hs.p, C, 0, -1, &ex));
+    }
     // ---- cross attention against the cached prompt K / V^T
-    Act ln2 = new_act(B, x.h, x.w, C);
-    TRY(add_layernorm(hs2, t + "norm2", ln2));
-    __half* wq2 = pack_rows(t + "attn2.q", {{t + "attn2.to_q.weight", head_perm(0)}}, C, s);
     __half* wk2 = pack_rows(t + "attn2.k", {{t + "attn2.to_k.weight", head_perm(0)}}, D, s);
     __half* wv2 = pack_rows(t + "attn2.v", {{t + "attn2.to_v.weight", head_perm(0)}}, D, s);
-    if (!wq2 || !wk2 || !wv2) return -1;
+    if (!wk2 || !wv2) return -1;
     __half* kc = static_cast<__half*>(prog.alloc((size_t)L * Cp * 2));
     const int Lpad = 128 * ((L + 127) / 128);
     __half* vct = static_cast<__half*>(prog.alloc((size_t)Cp * Lpad * 2));
@@ -700,12 +760,22 @@ int b2sd_engine::build_transformer(const std::string& p, const Act& x, int heads
         d.w = ctx; d.w_rows = L; d.w_ld = D; d.stride = 1;
         d.Nb = 1; d.Ho = 1; d.Wo = Cp;
         d.epi.out = vct; d.epi.ldc = Lpad; d.epi.acc_scale = 1.f; d.epi.res_scale = 1.f; d.epi.n_valid = L;
-        d.epi.flags = IG_CONST_A;
         TRY(add_igemm(prog_prompt, d));
         allow_swap = true;
     }
     Act q2 = new_act(1, 1, (int)M, Cp);
-    TRY(add_linear(prog_frame, tokens(ln2), wq2, Cp, C, nullptr, q2.p, Cp, nullptr, 0));
+    if (fold) {
+        LnFold f;
+        TRY(fold_ln(t + "attn2.q+ln", {{t + "attn2.to_q.weight", head_perm(0)}}, C, t + "norm2", nullptr, &f, s));
+        LinExtra ex; ex.rowstat_in = st2; ex.colsum = f.colsum; ex.ln_c = C;
+        TRY(add_linear(prog_frame, tokens(hs2), f.w, Cp, C, f.bias, q2.p, Cp, nullptr, 0, 0, -1, &ex));
+    } else {
+        Act ln2 = new_act(B, x.h, x.w, C);
+        TRY(add_layernorm(hs2, t + "norm2", ln2));
+        __half* wq2 = pack_rows(t + "attn2.q", {{t + "attn2.to_q.weight", head_perm(0)}}, C, s);
+        if (!wq2) return -1;
+        TRY(add_linear(prog_frame, tokens(ln2), wq2, Cp, C, nullptr, q2.p, Cp, nullptr, 0));
+    }
     Act ao2 = new_act(B, x.h, x.w, C);
     {
         AttnDesc a{};
@@ -723,37 +793,37 @@ int b2sd_engine::build_transformer(const std::string& p, const Act& x, int heads
     const Raw* wo2 = get(t + "attn2.to_out.0.weight");
     if (!wo2) return -1;
     Act hs3 = new_act(B, x.h, x.w, C);
-    TRY(add_linear(prog_frame, tokens(ao2), wo2->p, C, C, vec({t + "attn2.to_out.0.bias"}), hs3.p, C, hs2.p, C));
-    // ---- GEGLU feed-forward; weight rows interleaved per 128-wide tile as [64 value | 64 gate]
-    Act ln3 = new_act(B, x.h, x.w, C);
-    TRY(add_layernorm(hs3, t + "norm3", ln3));
-    const int inner = 4 * C;
-    std::vector<int> gperm;
     {
-        // tile width is chosen by add_igemm among {256,128,64}; use a fixed 128-column interleave (valid for
-        // BN=128 only) -> force BN through candidates: inner*2 % 128 == 0 always holds here
-        const int half = 64;
-        for (int tI = 0; tI < inner / half; ++tI) {
-            for (int i = 0; i < half; ++i) gperm.push_back(tI * half + i);
-            for (int i = 0; i < half; ++i) gperm.push_back(inner + tI * half + i);
-        }
+        LinExtra ex; ex.rowstat_out = st3;
+        TRY(add_linear(prog_frame, tokens(ao2), wo2->p, C, C, vec({t + "attn2.to_out.0.bias"}), hs3.p, C, hs2.p, C, 0, -1, &ex));
     }
-    __half* wff1 = pack_rows(t + "ff1", {{t + "ff.net.0.proj.weight", gperm}}, C, s);
-    const float* bff1 = vec({t + "ff.net.0.proj.bias"}, &gperm);
-    if (!wff1 || !bff1) return -1;
+    // ---- GEGLU feed-forward
     Act ff = new_act(1, 1, (int)M, inner);
     {
         IgemmDesc d{};
-        d.nseg = 1; d.src[0] = tokens(ln3); d.ntap[0] = 1;
-        d.w = wff1; d.w_rows = 2 * inner; d.w_ld = C; d.stride = 1;
+        d.nseg = 1; d.ntap[0] = 1;
+        d.w_rows = 2 * inner; d.w_ld = C; d.stride = 1;
         d.Nb = 1; d.Ho = 1; d.Wo = (int)M;
-        d.BN = 128;
-        d.epi.out = ff.p; d.epi.ldc = inner; d.epi.colbias = bff1; d.epi.acc_scale = 1.f; d.epi.res_scale = 1.f;
+        d.BN = 128;   // the 128-column value/gate interleave of the packed rows
+        d.epi.out = ff.p; d.epi.ldc = inner; d.epi.acc_scale = 1.f; d.epi.res_scale = 1.f;
         d.epi.flags = IG_GEGLU; d.epi.n_valid = inner;
-        if (!getenv("B2_NO_EARLY")) d.epi.flags |= IG_CONST_B;
+        if (fold) {
+            LnFold f;
+            TRY(fold_ln(t + "ff1+ln", {{t + "ff.net.0.proj.weight", gperm}}, C, t + "norm3", bff1, &f, s));
+            d.src[0] = tokens(hs3);
+            d.w = f.w; d.epi.colbias = f.bias;
+            d.epi.rowstat_in = st3; d.epi.colsum = f.colsum; d.epi.ln_inv_c = 1.f / (float)C; d.epi.ln_eps = 1e-5f;
+        } else {
+            Act ln3 = new_act(B, x.h, x.w, C);
+            TRY(add_layernorm(hs3, t + "norm3", ln3));
+            __half* wff1 = pack_rows(t + "ff1", {{t + "ff.net.0.proj.weight", gperm}}, C, s);
+            if (!wff1) return -1;
+            d.src[0] = tokens(ln3);
+            d.w = wff1; d.epi.colbias = bff1;
+        }
         IgemmPlan plan;
         TRY(igemm_plan(d, &plan));
-        push_igemm(prog_frame, plan, d, "igemm geglu " + p, 2.0 * (double)M * (2.0 * inner) * C);
+        push_igemm(prog_frame, plan, "igemm geglu " + p, 2.0 * (double)M * (2.0 * inner) * C);
     }
     const Raw* wff2 = get(t + "ff.net.2.weight");
     if (!wff2) return -1;
@@ -787,6 +857,20 @@ int b2sd_engine::build_program(cudaStream_t s) {
     const int B = cfg.batch, H = cfg.height, W = cfg.width;
     const int* ch = cfg.block_out_channels;
     const int nlev = 4;
+    {
+        // LayerNorm row statistics of every transformer block (3 per block, [tokens][2] 64-bit words), one slab that a single
+        // memset node clears at the start of each frame
+        long words = 0;
+        for (int i = 0; i < nlev; ++i) {
+            const long tokens_i = (long)B * (lh >> i) * (lw >> i);
+            const int blocks_i = (cfg.down_attn[i] ? cfg.layers_per_block + (cfg.layers_per_block + 1) : 0) + (i == nlev - 1 ? 1 : 0);
+            words += 3 * 2 * tokens_i * blocks_i;
+        }
+        ln_stats_cap = (size_t)words;
+        ln_stats_used = 0;
+        ln_stats = static_cast<unsigned long long*>(prog.alloc(ln_stats_cap * sizeof(unsigned long long)));
+        if (!ln_stats) return -1;
+    }
 
     allow_swap = false;
     // ================= TAESD encoder (EncoderTiny) =================
@@ -955,7 +1039,13 @@ int b2sd_engine::build_program(cudaStream_t s) {
     }
     taps["image"] = image;
     ++launches;  // post_u8 tail
-    link_weight_prefetch(prog_frame);
+    if (ln_stats_used) {
+        unsigned long long* sp = ln_stats;
+        const size_t bytes = ln_stats_used * sizeof(unsigned long long);
+        prog_frame.insert(prog_frame.begin(), Op([sp, bytes](cudaStream_t st) {
+            if (cudaMemsetAsync(sp, 0, bytes, st) != cudaSuccess) { b2_set_error("memset of the LayerNorm statistics failed"); return -1; }
+            return 0; }, "memset ln_stats"));
+    }
     CUDA_OK(cudaStreamSynchronize(s));
     built = true;
     return 0;

@@ -25,10 +25,28 @@ __device__ __forceinline__ void store_half16(__half* dst, const float* v, int nv
     }
 }
 
+// LayerNorm statistics of row `orow` from the fixed-point sums its producer accumulated (see IgEpilogue)
+__device__ __forceinline__ void ln_row_stats(const IgEpilogue& e, long orow, bool row_ok, float& mu, float& rstd) {
+    mu = 0.f;
+    rstd = 1.f;
+    if (!e.rowstat_in || !row_ok) return;
+    const ulonglong2 st = *reinterpret_cast<const ulonglong2*>(e.rowstat_in + 2 * orow);
+    const float s1 = (float)((double)(long long)st.x * (1.0 / IG_STAT_SCALE));
+    const float s2 = (float)((double)(long long)st.y * (1.0 / IG_STAT_SCALE));
+    mu = s1 * e.ln_inv_c;
+    const float var = fmaxf(s2 * e.ln_inv_c - mu * mu, 0.f);
+    rstd = rsqrtf(var + e.ln_eps);
+}
+__device__ __forceinline__ void rowstat_add(const IgEpilogue& e, long orow, float s1, float s2) {
+    atomicAdd(e.rowstat_out + 2 * orow, (unsigned long long)__float2ll_rn(s1 * IG_STAT_SCALE));
+    atomicAdd(e.rowstat_out + 2 * orow + 1, (unsigned long long)__float2ll_rn(s2 * IG_STAT_SCALE));
+}
+
 // 16 accumulator columns [col0, col0+16) of output row `orow` (batch item b); the accumulators are
 // acc[OFF .. OFF+16) of a register array (compile-time indices only: nothing may spill to local memory).
 template <int OFF, int N, typename T>
-__device__ __forceinline__ void epi_store16(const IgEpilogue& e, const T (&acc)[N], int b, long orow, int col0) {
+__device__ __forceinline__ void epi_store16(const IgEpilogue& e, const T (&acc)[N], int b, long orow, int col0, float mu = 0.f,
+                                            float rstd = 1.f) {
     int nv = e.n_valid - col0;
     if (nv <= 0) return;
     if (nv > 16) nv = 16;
@@ -37,6 +55,12 @@ __device__ __forceinline__ void epi_store16(const IgEpilogue& e, const T (&acc)[
     for (int i = 0; i < 16; ++i) {
         if constexpr (sizeof(T) == 4 && !__is_same(T, float)) v[i] = __uint_as_float(acc[OFF + i]);
         else v[i] = acc[OFF + i];
+    }
+    if (e.colsum) {   // folded LayerNorm of the A rows
+        const float* cs = e.colsum + col0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (i < nv) v[i] = rstd * (v[i] - mu * cs[i]);
     }
     if (e.colbias) {
         const float* bp = e.colbias + (long)b * e.colbias_bstride + col0;
@@ -79,6 +103,24 @@ __device__ __forceinline__ void epi_store16(const IgEpilogue& e, const T (&acc)[
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
     }
+    if (e.out2 && col0 >= e.col2) {   // V block of the fused q/k/v projection: transposed store (32 lanes = 32 consecutive tokens)
+        __half* tp = e.out2 + (long)(col0 - e.col2) * e.ld2 + orow;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (i < nv) tp[(long)i * e.ld2] = __float2half_rn(v[i]);
+        return;
+    }
+    if (e.rowstat_out) {   // statistics of the values as stored (fp16-rounded), like a LayerNorm reading them back
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (i < nv) {
+                const float x = __half2float(__float2half_rn(v[i]));
+                s1 += x;
+                s2 += x * x;
+            }
+        rowstat_add(e, orow, s1, s2);
+    }
     store_half16(e.out + orow * e.ldc + col0, v, nv, (e.ldc & 7) == 0);
 }
 
@@ -86,11 +128,15 @@ __device__ __forceinline__ void epi_store16(const IgEpilogue& e, const T (&acc)[
 // uses packed indexing), output column index is ocol0.
 __device__ __forceinline__ void epi_store16_geglu(const IgEpilogue& e, const uint32_t (&val)[16],
                                                   const uint32_t (&gate)[16], long orow, int pcol_val,
-                                                  int pcol_gate, int ocol0) {
+                                                  int pcol_gate, int ocol0, float mu = 0.f, float rstd = 1.f) {
     float v[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         float a = __uint_as_float(val[i]), g = __uint_as_float(gate[i]);
+        if (e.colsum) {   // folded LayerNorm (norm3) of the A rows
+            a = rstd * (a - mu * e.colsum[pcol_val + i]);
+            g = rstd * (g - mu * e.colsum[pcol_gate + i]);
+        }
         if (e.colbias) {
             a += e.colbias[pcol_val + i];
             g += e.colbias[pcol_gate + i];
@@ -128,6 +174,7 @@ __device__ __forceinline__ void epi_row_fast(const IgEpilogue& e, uint32_t taddr
                 if (c + 4 * i < ncols) b8[i] = reinterpret_cast<const float4*>(bp + c)[i];
         }
     };
+    float st1 = 0.f, st2 = 0.f;
     fetch(0, rr, bb);
     if (wait_bar) {
         mbar_wait(wait_bar, wait_parity);
@@ -171,6 +218,11 @@ __device__ __forceinline__ void epi_row_fast(const IgEpilogue& e, uint32_t taddr
                             x1 = fmaxf(x1, 0.f);
                         }
                         oh[j] = __floats2half2_rn(x0, x1);
+                        if (e.rowstat_out) {   // LayerNorm statistics of the stored (fp16-rounded) row
+                            const float2 f = __half22float2(oh[j]);
+                            st1 += f.x + f.y;
+                            st2 += f.x * f.x + f.y * f.y;
+                        }
                     }
                     reinterpret_cast<uint4*>(op + c)[g] = o;
                 }
@@ -181,11 +233,12 @@ __device__ __forceinline__ void epi_row_fast(const IgEpilogue& e, uint32_t taddr
 #pragma unroll
         for (int i = 0; i < 8; ++i) bb[i] = bn[i];
     }
+    if (e.rowstat_out && row_ok && ncols > 0) rowstat_add(e, orow, st1, st2);
 }
 
 __device__ __forceinline__ bool epi_fast_ok(const IgEpilogue& e) {
     return !(e.flags & (IG_SPLITK | IG_GEGLU)) && (e.n_valid & 15) == 0 && (e.ldc & 7) == 0 && (!e.res || (e.ldr & 7) == 0) &&
-           (e.colbias_bstride & 3) == 0;
+           (e.colbias_bstride & 3) == 0 && !e.colsum && !e.out2;
 }
 
 }  // namespace b2

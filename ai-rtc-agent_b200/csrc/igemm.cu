@@ -140,7 +140,7 @@ __device__ __forceinline__ void splitk_sum16(uint32_t stg_local, int cc, int row
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(IG_THREADS, IG_THREADS <= 192 ? 2 : 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
+__global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant__ IgemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~static_cast<uintptr_t>(1023));
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(IG_THREADS, IG_THREADS <= 192 ? 2 : 1) igemm_k
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full_bar[s], 1);
-            mbar_init(&tmem_empty_bar[s], IG_EPI_THREADS);
+            mbar_init(&tmem_empty_bar[s], 128);
         }
         fence_mbar_init();
     }
@@ -184,69 +184,6 @@ __global__ void __launch_bounds__(IG_THREADS, IG_THREADS <= 192 ? 2 : 1) igemm_k
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // ---- TMA producer helpers (used by warp 0 / lane 0 only).  The k-block cursor walks (segment, tap, channel block).
-    struct KCursor { int seg, tap, cb; };
-    auto cursor_at = [&](int kb0) {
-        KCursor c{0, 0, 0};
-        int base = 0;
-        while (c.seg < p.nseg - 1 && kb0 >= base + p.seg_ntap[c.seg] * p.seg_cblocks[c.seg]) {
-            base += p.seg_ntap[c.seg] * p.seg_cblocks[c.seg];
-            ++c.seg;
-        }
-        c.tap = (kb0 - base) / p.seg_cblocks[c.seg];
-        c.cb = (kb0 - base) % p.seg_cblocks[c.seg];
-        return c;
-    };
-    auto cursor_next = [&](KCursor& c) {
-        if (++c.cb == p.seg_cblocks[c.seg]) {
-            c.cb = 0;
-            if (++c.tap == p.seg_ntap[c.seg]) {
-                c.tap = 0;
-                ++c.seg;
-            }
-        }
-    };
-    // normal: pixels -> A region (M side), weights -> B region.  swapped: weights (128 output channels) -> A region, pixels -> B
-    struct TileOrg { int w0, h0, n0; };
-    auto tile_origin = [&](int mt) {   // integer divisions: once per M tile, never per k-block (the producer's issue rate matters)
-        TileOrg t;
-        t.w0 = (mt % p.tiles_w) * p.tw * p.stride;
-        t.h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th * p.stride;
-        t.n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
-        return t;
-    };
-    auto load_src = [&](int stage, const KCursor& c, const TileOrg& t) {   // the 4-D "activation view" operand (tmA)
-        uint8_t* sa = smem + (size_t)stage * stage_bytes;
-        int dy = 0, dx = 0;
-        if (p.seg_ntap[c.seg] == 9) {
-            dy = c.tap / 3 - 1;
-            dx = c.tap % 3 - 1;
-        }
-        tma_load_4d(p.swap ? sa + IG_BM * IG_BK * 2 : sa, &p.tmA[c.seg], &full_bar[stage], p.seg_c0[c.seg] + c.cb * IG_BK,
-                    t.w0 + dx, t.h0 + dy, t.n0);
-    };
-    auto load_w = [&](int stage, int kb) {                        // the 2-D "weight matrix" operand (tmB)
-        uint8_t* sa = smem + (size_t)stage * stage_bytes;
-        tma_load_2d(p.swap ? sa : sa + IG_BM * IG_BK * 2, &p.tmB, &full_bar[stage], kb * IG_BK, ntile * (p.swap ? IG_BM : p.BN));
-    };
-    // Operands that no earlier kernel of the stream writes (packed weights) do not have to wait for the programmatic
-    // dependency: the first ring pass of weight tiles is requested BEFORE griddepcontrol.wait, so its HBM latency overlaps the
-    // tail of the previous kernel, and the weights of the NEXT contraction of the frame are pulled into L2 (p.pf_*).
-    int early = 0;
-    if (warp == 0) {
-        if (p.pf_bytes) l2_prefetch_slice(p.pf_ptr, p.pf_bytes, lane);
-        if (lane == 0 && (p.epi.flags & (IG_CONST_B | IG_CONST_A)) && (int)blockIdx.x < num_mtiles && p.dbg_mode == 0) {
-            early = min(p.num_stages, kb_end - kb_begin);
-            KCursor c = cursor_at(kb_begin);
-            const TileOrg t0 = tile_origin(blockIdx.x);
-            for (int s = 0; s < early; ++s) {
-                mbar_expect_tx(&full_bar[s], p.a_bytes + p.b_bytes);
-                if (p.epi.flags & IG_CONST_B) load_w(s, kb_begin + s);
-                if (p.epi.flags & IG_CONST_A) load_src(s, c, t0);
-                cursor_next(c);
-            }
-        }
-    }
     pdl_launch_dependents();   // the next kernel may start its own prologue now
     pdl_wait();                // ... and everything below reads the previous kernel's output
     B2_TS(if (ts && threadIdx.x == 0) ts[1] = globaltimer_ns();)
@@ -257,11 +194,16 @@ __global__ void __launch_bounds__(IG_THREADS, IG_THREADS <= 192 ? 2 : 1) igemm_k
             // ===== TMA producer =====
             int stage = 0;
             uint32_t phase = 0;
-            const bool early_a = (p.epi.flags & IG_CONST_A) != 0, early_b = (p.epi.flags & IG_CONST_B) != 0;
             for (int mt = blockIdx.x; mt < num_mtiles; mt += gridDim.x) {
-                KCursor c = cursor_at(kb_begin);
-                const TileOrg torg = tile_origin(mt);
-                int armed_left = mt == (int)blockIdx.x ? early : 0;   // k-blocks of this tile whose constant operand is already in flight
+                const int w0 = (mt % p.tiles_w) * p.tw, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
+                const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
+                int seg = 0, base = 0;
+                while (seg < p.nseg - 1 && kb_begin >= base + p.seg_ntap[seg] * p.seg_cblocks[seg]) {
+                    base += p.seg_ntap[seg] * p.seg_cblocks[seg];
+                    ++seg;
+                }
+                int tap = (kb_begin - base) / p.seg_cblocks[seg];
+                int cb = (kb_begin - base) % p.seg_cblocks[seg];
                 for (int kb = kb_begin; kb < kb_end; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
 #ifdef B2_BOUND_STUDY
@@ -271,13 +213,26 @@ __global__ void __launch_bounds__(IG_THREADS, IG_THREADS <= 192 ? 2 : 1) igemm_k
                         continue;
                     }
 #endif
-                    const bool armed = armed_left > 0;   // requested before the PDL wait
-                    armed_left -= armed;
-                    if (!armed) mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
-                    if (!(armed && early_a)) load_src(stage, c, torg);
-                    if (!(armed && early_b)) load_w(stage, kb);
+                    mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
+                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                    uint8_t* sb = sa + IG_BM * IG_BK * 2;
+                    int dy = 0, dx = 0;
+                    if (p.seg_ntap[seg] == 9) {
+                        dy = tap / 3 - 1;
+                        dx = tap % 3 - 1;
+                    }
+                    // normal: pixels -> A (M side), weights -> B.  swapped: weights (128 output channels) -> A, pixels -> B
+                    tma_load_4d(p.swap ? sb : sa, &p.tmA[seg], &full_bar[stage], p.seg_c0[seg] + cb * IG_BK,
+                                w0 * p.stride + dx, h0 * p.stride + dy, n0);
+                    tma_load_2d(p.swap ? sa : sb, &p.tmB, &full_bar[stage], kb * IG_BK, ntile * (p.swap ? IG_BM : p.BN));
                     B2_TS(if (ts && mt == (int)blockIdx.x && kb == kb_begin) ts[2] = globaltimer_ns();)
-                    cursor_next(c);
+                    if (++cb == p.seg_cblocks[seg]) {
+                        cb = 0;
+                        if (++tap == p.seg_ntap[seg]) {
+                            tap = 0;
+                            ++seg;
+                        }
+                    }
                     if (++stage == p.num_stages) {
                         stage = 0;
                         phase ^= 1;
@@ -333,11 +288,7 @@ __global__ void __launch_bounds__(IG_THREADS, IG_THREADS <= 192 ? 2 : 1) igemm_k
         }
     } else {
         // ===== epilogue: TMEM -> registers -> global =====
-        // Optional second set of four epilogue warps (-DIG_THREADS=320: warps 6-9 see the same four TMEM lane quarters as 2-5
-        // and take the other half of a tile's columns).  Default build: one set -- 320 threads x 168 registers would leave
-        // one CTA per SM, and the co-residency of two CTAs (PDL overlap, persistent launches) is worth more.
         const int q = warp & 3;  // TMEM lane quarter this warp may access
-        const int eset = (IG_ESETS == 2 && warp >= 6) ? 1 : 0;
         const int r = q * 32 + lane;
         const int wi = r % p.tw;
         const int hi = (r / p.tw) % p.th;
@@ -358,7 +309,7 @@ __global__ void __launch_bounds__(IG_THREADS, IG_THREADS <= 192 ? 2 : 1) igemm_k
                 tc_fence_after();
                 if (e.flags & IG_SPLITK) {
                     float4* stg = reinterpret_cast<float4*>(smem);
-                    for (int c = eset * 16; c < p.BN; c += 16 * IG_ESETS) {
+                    for (int c = 0; c < p.BN; c += 16) {
                         uint32_t v[16];
                         tmem_ld16(taddr + c, v);
                         tmem_ld_wait();
@@ -367,7 +318,7 @@ __global__ void __launch_bounds__(IG_THREADS, IG_THREADS <= 192 ? 2 : 1) igemm_k
                             stg[((c >> 2) + i) * IG_BM + r] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
                                                                           __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
                     }
-                } else if (eset == 0) {
+                } else {
                     // the operand ring is idle (every MMA has retired): use its head as the transposition tile
                     float* T = reinterpret_cast<float*>(smem);
                     for (int c = 0; c < p.BN; c += SWAP_CH) {
@@ -386,10 +337,7 @@ __global__ void __launch_bounds__(IG_THREADS, IG_THREADS <= 192 ? 2 : 1) igemm_k
             } else if (epi_fast_ok(e)) {
                 int ncols = e.n_valid - ntile * p.BN;
                 if (ncols > p.BN) ncols = p.BN;
-                if (ncols < 0) ncols = 0;
-                const int csplit = IG_ESETS == 2 ? min(ncols, ((ncols >> 1) + 31) & ~31) : ncols;   // set 0: [0, csplit), set 1: [csplit, ncols)
-                const int c0 = eset ? csplit : 0, cn = eset ? ncols - csplit : csplit;
-                epi_row_fast(e, taddr + c0, cn, ntile * p.BN + c0, n, orow, row_ok && cn > 0, &tmem_full_bar[buf], par);
+                epi_row_fast(e, taddr, ncols, ntile * p.BN, n, orow, row_ok && ncols > 0, &tmem_full_bar[buf], par);
             } else {
                 mbar_wait(&tmem_full_bar[buf], par);
                 tc_fence_after();
@@ -399,7 +347,7 @@ __global__ void __launch_bounds__(IG_THREADS, IG_THREADS <= 192 ? 2 : 1) igemm_k
                     // these stores and the peers' DSMEM reads are conflict-free; the reduction happens after the cluster
                     // barrier below.
                     float4* stg = reinterpret_cast<float4*>(smem);
-                    for (int c = eset * 16; c < p.BN; c += 16 * IG_ESETS) {
+                    for (int c = 0; c < p.BN; c += 16) {
                         uint32_t v[16];
                         tmem_ld16(taddr + c, v);
                         tmem_ld_wait();
@@ -410,30 +358,34 @@ __global__ void __launch_bounds__(IG_THREADS, IG_THREADS <= 192 ? 2 : 1) igemm_k
                     }
                 } else if (e.flags & IG_GEGLU) {
                     const int half_n = p.BN / 2;
-                    for (int c = eset * 16; c < half_n; c += 16 * IG_ESETS) {
+                    float mu, rstd;
+                    ln_row_stats(e, orow, row_ok, mu, rstd);
+                    for (int c = 0; c < half_n; c += 16) {
                         uint32_t a[16], g[16];
                         tmem_ld16(taddr + c, a);
                         tmem_ld16(taddr + half_n + c, g);
                         tmem_ld_wait();
                         if (row_ok)
-                            epi_store16_geglu(e, a, g, orow, ntile * p.BN + c, ntile * p.BN + half_n + c, ntile * half_n + c);
+                            epi_store16_geglu(e, a, g, orow, ntile * p.BN + c, ntile * p.BN + half_n + c, ntile * half_n + c, mu, rstd);
                     }
                 } else {
-                    for (int c = eset * 32; c + 32 <= p.BN; c += 32 * IG_ESETS) {
+                    float mu, rstd;
+                    ln_row_stats(e, orow, row_ok, mu, rstd);
+                    for (int c = 0; c + 32 <= p.BN; c += 32) {
                         uint32_t v[32];
                         tmem_ld32(taddr + c, v);
                         tmem_ld_wait();
                         if (row_ok) {
-                            epi_store16<0>(e, v, n, orow, ntile * p.BN + c);
-                            epi_store16<16>(e, v, n, orow, ntile * p.BN + c + 16);
+                            epi_store16<0>(e, v, n, orow, ntile * p.BN + c, mu, rstd);
+                            epi_store16<16>(e, v, n, orow, ntile * p.BN + c + 16, mu, rstd);
                         }
                     }
-                    if ((p.BN & 31) && eset == 0) {   // 16-column tail
+                    if (p.BN & 31) {   // 16-column tail
                         const int c = p.BN & ~31;
                         uint32_t v[16];
                         tmem_ld16(taddr + c, v);
                         tmem_ld_wait();
-                        if (row_ok) epi_store16<0>(e, v, n, orow, ntile * p.BN + c);
+                        if (row_ok) epi_store16<0>(e, v, n, orow, ntile * p.BN + c, mu, rstd);
                     }
                 }
             }
@@ -454,7 +406,6 @@ __global__ void __launch_bounds__(IG_THREADS, IG_THREADS <= 192 ? 2 : 1) igemm_k
         cluster_sync_all();  // all partial tiles are in place (release/acquire over the cluster)
         B2_TS(if (ts && threadIdx.x == 64) ts[6] = globaltimer_ns();)   // split launches: [5] staged, [6] cluster barrier passed, [7] reduced
         if (warp >= 2 && p.swap) {
-          if (warp < 6) {   // the transposition tile is swept by 128 threads (named barrier 1)
             // swapped orientation: this CTA finalises the pixel columns [rank*cols_per, (rank+1)*cols_per) of the tile
             const int rank = (int)cluster_ctarank();
             const int cols_per = p.BN / splits;
@@ -498,14 +449,13 @@ __global__ void __launch_bounds__(IG_THREADS, IG_THREADS <= 192 ? 2 : 1) igemm_k
                 swap_store_chunk(p, pre, T, ntile, t);
                 epi_bar_sync();
             }
-          }
         } else if (warp >= 2) {
             const int rank = (int)cluster_ctarank();
             const int rows_per = IG_BM / splits;          // splits in {2,4,8}
-            const int t = threadIdx.x - 64;               // 0..255
+            const int t = threadIdx.x - 64;               // 0..127
             const int chunks = p.BN >> 4;
             const uint32_t stg_local = smem_u32(smem);
-            for (int item = t; item < rows_per * chunks; item += IG_EPI_THREADS) {
+            for (int item = t; item < rows_per * chunks; item += 128) {
                 const int rl = item % rows_per;
                 const int cc = item / rows_per;
                 const int r = rank * rows_per + rl;       // row of the tile this CTA finalises
@@ -518,7 +468,12 @@ __global__ void __launch_bounds__(IG_THREADS, IG_THREADS <= 192 ? 2 : 1) igemm_k
                     case 4: splitk_sum16<4>(stg_local, cc, r, acc); break;
                     default: splitk_sum16<8>(stg_local, cc, r, acc); break;
                 }
-                if (ok) epi_store16<0>(p.epi, acc, n, ((long)n * p.Ho + h) * p.Wo + w, ntile * p.BN + cc * 16);
+                if (ok) {
+                    const long orow = ((long)n * p.Ho + h) * p.Wo + w;
+                    float mu, rstd;
+                    ln_row_stats(p.epi, orow, true, mu, rstd);
+                    epi_store16<0>(p.epi, acc, n, orow, ntile * p.BN + cc * 16, mu, rstd);
+                }
             }
         }
         B2_TS(if (ts && threadIdx.x == 64) ts[7] = globaltimer_ns();)
@@ -601,8 +556,8 @@ size_t igemm_partial_floats(int splits, long rows_total, int n_valid) {
 // Swapped orientation plan: output channels on the M side (128 per CTA), a tile of BN pixels on the N side.
 static int plan_swap(const IgemmDesc& d, IgemmPlan* plan) {
     IgemmParams& p = plan->p;
-    if ((d.epi.flags & IG_GEGLU) || d.nseg < 1 || d.nseg > IG_MAX_SRC) {
-        b2_set_error("igemm(swap): unsupported (GEGLU / nseg %d)", d.nseg);
+    if ((d.epi.flags & IG_GEGLU) || d.nseg < 1 || d.nseg > IG_MAX_SRC || d.epi.rowstat_out || d.epi.colsum || d.epi.out2) {
+        b2_set_error("igemm(swap): unsupported (GEGLU / LayerNorm fold / row statistics / transposed V / nseg %d)", d.nseg);
         return -1;
     }
     int BN = d.BN;

@@ -18,21 +18,12 @@ constexpr int IG_BM = 128;        // rows (pixels/tokens) per CTA tile == UMMA M
 constexpr int IG_BK = 64;         // fp16 elements per K-block (128 B = one swizzle row)
 constexpr int IG_MAX_SRC = 3;
 constexpr int IG_MAX_STAGES = 8;
-#ifndef IG_THREADS_OVERRIDE
 constexpr int IG_THREADS = 192;   // warp0: TMA, warp1: MMA + TMEM alloc, warps 2-5: epilogue
-#else
-constexpr int IG_THREADS = IG_THREADS_OVERRIDE;   // 320: a second set of four epilogue warps (experiment)
-#endif
-constexpr int IG_EPI_THREADS = IG_THREADS - 64;
-constexpr int IG_ESETS = IG_EPI_THREADS / 128;
 
 enum : int {
     IG_RELU = 1,    // relu after bias/residual
     IG_GEGLU = 2,   // tile columns [0,BN/2) = value, [BN/2,BN) = gate; out = v * gelu_erf(g)
     IG_SPLITK = 4,  // set by the planner: K is split over a thread-block cluster, partial tiles are reduced through DSMEM
-    IG_CONST_B = 16,  // the weight-matrix operand (IgemmDesc::w) is never written by a kernel of the stream: it may be fetched
-                      // before the programmatic-dependency wait
-    IG_CONST_A = 32,  // same for the activation-view operand (src[]) -- the V^T GEMM, whose "activations" are the weights
 };
 
 struct IgEpilogue {
@@ -46,7 +37,24 @@ struct IgEpilogue {
     float res_scale;
     int flags;
     int n_valid;            // valid output columns (Cout)
+    // ---- LayerNorm without a LayerNorm launch (transformer blocks: diffusers attention.py BasicTransformerBlock norm1/2/3) ----
+    // producer side: besides storing its fp16 output rows, accumulate their (sum, sum of squares) as 2^20 fixed point in
+    // 64-bit integer atomics -- integer addition commutes, so the statistics are bit-reproducible whatever order the N tiles
+    // and split-K CTAs arrive in.  [rows][2], zeroed at the start of every frame.
+    unsigned long long* rowstat_out;
+    // consumer side: y = LN(x) W^T + b  ==  rstd_r * (x W'^T - mean_r * colsum) + bias'  with W' = W diag(gamma) (packed at load
+    // time), colsum[n] = sum_k W'[n][k], bias'[n] = sum_k W[n][k] beta[k] + b[n] (passed as colbias).  rowstat_in = the
+    // statistics of this GEMM's A rows written by its producer; ln_inv_c = 1 / C, ln_eps = 1e-5.
+    const unsigned long long* rowstat_in;
+    const float* colsum;
+    float ln_inv_c, ln_eps;
+    // ---- fused q/k/v projection: output columns >= col2 (the V block) are stored TRANSPOSED, out2[(col - col2) * ld2 + row],
+    // which is the K-major V^T operand the attention kernel's P.V MMA reads (was a separate swapped-operand GEMM launch)
+    __half* out2;
+    int ld2, col2;
 };
+
+constexpr float IG_STAT_SCALE = 1048576.f;   // 2^20 fixed point of the row statistics
 
 struct IgemmParams {
     CUtensorMap tmA[IG_MAX_SRC];
@@ -72,8 +80,6 @@ struct IgemmParams {
     int swap;                     // 1: weights on the M side (128 output channels per CTA), pixels on the N side
     int tw_log2, th_log2;         // swap mode: pixel-tile extents are powers of two
     int dbg_mode;                 // bound study (-DB2_BOUND_STUDY + env B2_DBG_MODE): 1 = TMA loads only for the first ring pass, 2 = no MMAs
-    const void* pf_ptr;           // weights of the NEXT contraction of the frame program: pulled into L2 while this one runs
-    unsigned long long pf_bytes;  // (0 = nothing to prefetch; multiple of 16)
     IgEpilogue epi;
 };
 

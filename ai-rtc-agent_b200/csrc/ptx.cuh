@@ -135,29 +135,6 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
-// L2 prefetch of a byte range (no smem destination, no completion tracking): sm_90+ bulk prefetch
-__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
-}
-// One warp of every CTA prefetches this CTA's share of [base, base + total): the grid covers the range once.
-__device__ __forceinline__ void l2_prefetch_slice(const void* base, unsigned long long total, int lane) {
-    const unsigned long long ncta = (unsigned long long)gridDim.x * gridDim.y * gridDim.z;
-    const unsigned long long cid = ((unsigned long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    const unsigned long long per = ((total + ncta - 1) / ncta + 511ull) & ~511ull;   // 32 lanes x 16-byte granules
-    const unsigned long long start = cid * per;
-    if (start >= total) return;
-    const unsigned long long len = total - start < per ? total - start : per;
-    const unsigned long long piece = ((len + 31) / 32 + 15ull) & ~15ull;
-    unsigned long long o = (unsigned long long)lane * piece;
-    const unsigned long long end = o + piece < len ? o + piece : len;
-    const char* b = static_cast<const char*>(base) + start;
-    while (o < end) {
-        const unsigned long long chunk = end - o < 16384ull ? end - o : 16384ull;
-        l2_prefetch_bulk(b + o, (uint32_t)chunk);
-        o += chunk;
-    }
-}
-
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(

@@ -30,6 +30,8 @@ class IgemmDesc(C.Structure):
         ("res", C.c_void_p), ("ldr", C.c_int),
         ("acc_scale", C.c_float), ("res_scale", C.c_float),
         ("flags", C.c_int), ("n_valid", C.c_int), ("swap", C.c_int),
+        ("rowstat_out", C.c_void_p), ("rowstat_in", C.c_void_p), ("colsum", C.c_void_p), ("ln_c", C.c_int), ("ln_eps", C.c_float),
+        ("out2", C.c_void_p), ("ld2", C.c_int), ("col2", C.c_int),
     ]
 
 
@@ -67,8 +69,6 @@ IN_U8_NHWC, IN_F32_NCHW, IN_F16_NCHW = 0, 1, 2
 OUT_U8_NCHW, OUT_F16_NCHW = 0, 1
 IG_RELU = 1
 IG_GEGLU = 2
-IG_CONST_W = 16
-IG_CONST_SRC = 32
 IG_TCONV = 64
 
 _lib = None

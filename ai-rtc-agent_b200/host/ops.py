@@ -32,7 +32,10 @@ def igemm(srcs: Sequence[Tuple[torch.Tensor, int]], w: torch.Tensor, out: torch.
           stride: int = 1, colbias: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
           acc_scale: float = 1.0, res_scale: float = 1.0, relu: bool = False, geglu: bool = False,
           bn: int = 0, splits: int = 1, n_valid: Optional[int] = None, timeline: Optional[torch.Tensor] = None, swap: bool = False,
-          const_w: bool = False, const_src: bool = False, tconv: bool = False) -> torch.Tensor:
+          tconv: bool = False,
+          rowstat_out: Optional[torch.Tensor] = None, rowstat_in: Optional[torch.Tensor] = None,
+          colsum: Optional[torch.Tensor] = None, ln_c: int = 0, ln_eps: float = 1e-5,
+          out2: Optional[torch.Tensor] = None, col2: int = 0) -> torch.Tensor:
     """srcs: [(NHWC fp16 tensor, ntap)], w: packed fp16 [rows, K]; out: NHWC fp16 [nb,ho,wo,ldc>=n]."""
     d = capi.IgemmDesc()
     d.nseg = len(srcs)
@@ -59,8 +62,16 @@ def igemm(srcs: Sequence[Tuple[torch.Tensor, int]], w: torch.Tensor, out: torch.
         assert res.dtype == torch.float16
         d.res, d.ldr = res.data_ptr(), res.stride(2)
     d.acc_scale, d.res_scale = acc_scale, res_scale
-    d.flags = ((capi.IG_RELU if relu else 0) | (capi.IG_GEGLU if geglu else 0) | (capi.IG_CONST_W if const_w else 0) |
-               (capi.IG_CONST_SRC if const_src else 0) | (capi.IG_TCONV if tconv else 0))
+    d.flags = (capi.IG_RELU if relu else 0) | (capi.IG_GEGLU if geglu else 0) | (capi.IG_TCONV if tconv else 0)
+    if rowstat_out is not None:
+        assert rowstat_out.dtype == torch.int64 and rowstat_out.is_contiguous()
+        d.rowstat_out = rowstat_out.data_ptr()
+    if rowstat_in is not None:
+        assert rowstat_in.dtype == torch.int64 and colsum is not None and colsum.dtype == torch.float32 and ln_c > 0
+        d.rowstat_in, d.colsum, d.ln_c, d.ln_eps = rowstat_in.data_ptr(), colsum.data_ptr(), ln_c, ln_eps
+    if out2 is not None:
+        assert out2.dtype == torch.float16 and out2.dim() == 2 and out2.stride(1) == 1
+        d.out2, d.ld2, d.col2 = out2.data_ptr(), out2.stride(0), col2
     capi.check(capi.lib().b2sd_op_igemm(C.byref(d), capi.current_stream_ptr()), "b2sd_op_igemm")
     return out
 

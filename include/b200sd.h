@@ -40,9 +40,6 @@ typedef struct {
 enum {
     B2SD_IG_RELU = 1,
     B2SD_IG_GEGLU = 2,
-    B2SD_IG_CONST_W = 16,    /* hint: `w` is never written by a kernel of the stream (packed weights): it may be fetched
-                                before the programmatic-dependency wait of the launch */
-    B2SD_IG_CONST_SRC = 32,  /* same hint for src[] (the V^T GEMM, whose "activation view" is a weight matrix) */
     B2SD_IG_TCONV = 64       /* run the persistent halo-tile kernel (stride-1 3x3, 64 -> 64 channels: the TAESD body) */
 };
 
@@ -71,6 +68,20 @@ typedef struct {
     int flags;
     int n_valid;       /* output channels */
     int swap;          /* 1: swapped orientation (output channels on the MMA M side, bn = 64/128/256 pixels on N) */
+    /* LayerNorm without a LayerNorm launch (BasicTransformerBlock norm1/2/3), all optional (NULL / 0 = off):
+     * rowstat_out  producer: also accumulate (sum, sum of squares) of every stored fp16 output row as 2^20 fixed point into
+     *              uint64 [rows][2] with integer atomics (order independent => bit reproducible); caller zeroes it;
+     * rowstat_in   consumer: those statistics for this GEMM's A rows; with colsum[n] = sum_k w[n][k] (w = W diag(gamma)) and
+     *              colbias[n] = sum_k W[n][k] beta[k] + b[n] the epilogue computes rstd*(acc - mean*colsum) + colbias,
+     *              i.e. LayerNorm(A) W^T + b, mean/var over ln_c columns with eps ln_eps;
+     * out2         columns >= col2 are stored transposed, out2[(col - col2)*ld2 + row] (V^T block of a fused q/k/v projection). */
+    void* rowstat_out;
+    const void* rowstat_in;
+    const float* colsum;
+    int ln_c;
+    float ln_eps;
+    void* out2;
+    int ld2, col2;
 } b2sd_igemm_desc;
 
 int b2sd_op_igemm(const b2sd_igemm_desc* d, void* stream);

@@ -246,24 +246,103 @@ def test_tconv_rejects_other_shapes(cuda):
         ops.igemm([(x, 9)], wp, out, tconv=True)
 
 
-@pytest.mark.parametrize("const_w,const_src", [(True, False), (False, True)])
-@pytest.mark.parametrize("nb,h,w,cin,cout,splits,swap", [
-    (1, 64, 64, 320, 320, 1, False),    # ring deeper than needed for the first pass
-    (1, 16, 16, 1280, 1280, 4, False),  # split-K slices start at different k-blocks
-    (1, 8, 8, 1280, 1280, 8, True),     # swapped orientation: the weight operand sits in the A region
-    (1, 256, 256, 64, 64, 1, False),    # persistent launch: only the first tile's loads are issued early
-])
-def test_conv3x3_early_constant_operand(cuda, nb, h, w, cin, cout, splits, swap, const_w, const_src):
-    """IG_CONST_W / IG_CONST_SRC: the constant operand's first ring pass is requested before griddepcontrol.wait.
-    Result must be bit-identical to the plain launch."""
+# ---- LayerNorm folded into the consumer GEMM + fused q/k/v projection (BasicTransformerBlock without layernorm launches) ----
+STAT_SCALE = float(1 << 20)
+
+
+def _ln_fold_operands(w16, gamma, beta, bias):
+    """What the engine prepares at load time (engine.cu fold_ln): W' = W diag(gamma) in fp16, colsum over the ROUNDED W',
+    bias' = W beta + b."""
+    wp = (w16.float() * gamma[None, :]).to(torch.float16).contiguous()
+    colsum = wp.float().sum(dim=1).contiguous()
+    bprime = (w16.float() @ beta + (bias if bias is not None else 0)).float().contiguous()
+    return wp, colsum, bprime
+
+
+@pytest.mark.parametrize("m,k,n,splits", [(4096, 320, 320, 1), (256, 1280, 1280, 4), (1000, 640, 640, 1)])
+def test_linear_row_statistics(cuda, m, k, n, splits):
+    """rowstat_out: (sum, sum of squares) of every stored fp16 row in 2^20 fixed point -- exactly what a LayerNorm reading the
+    row back would reduce; integer atomics => bit-identical across runs (N tiles / split-K CTAs arrive in any order)."""
     ops = _ops()
-    x = _nhwc16(_rand((nb, cin, h, w), cuda, 1))
-    wt = _rand((cout, cin, 3, 3), cuda, 2, 1.0 / math.sqrt(9 * cin)).to(torch.float16)
-    bias = _rand((nb, cout), cuda, 3).float().contiguous()
-    wp = ops.pack_conv_weight(wt)
-    bn = 256 if swap else 0
-    ref = torch.empty((nb, h, w, cout), dtype=torch.float16, device=cuda)
-    ops.igemm([(x, 9)], wp, ref, colbias=bias, splits=splits, swap=swap, bn=bn)
-    out = torch.full_like(ref, float("nan"))
-    ops.igemm([(x, 9)], wp, out, colbias=bias, splits=splits, swap=swap, bn=bn, const_w=const_w, const_src=const_src)
-    assert torch.equal(out, ref)
+    x = _rand((1, 1, m, k), cuda, 1).to(torch.float16)
+    w = _rand((n, k), cuda, 2, 1.0 / math.sqrt(k)).to(torch.float16)
+    bias = _rand((1, n), cuda, 3).float().contiguous()
+    res = _rand((1, 1, m, n), cuda, 4).to(torch.float16)
+    outs, stats = [], []
+    for _ in range(3):
+        out = torch.empty((1, 1, m, n), dtype=torch.float16, device=cuda)
+        st = torch.zeros((m, 2), dtype=torch.int64, device=cuda)
+        ops.igemm([(x, 1)], w, out, colbias=bias, res=res, splits=splits, rowstat_out=st)
+        outs.append(out)
+        stats.append(st)
+    assert torch.equal(stats[0], stats[1]) and torch.equal(stats[0], stats[2]) and torch.equal(outs[0], outs[1])
+    y = outs[0].reshape(m, n).double()
+    want = torch.stack([y.sum(1), (y * y).sum(1)], dim=1)
+    got = stats[0].double() / STAT_SCALE
+    assert_close(got, want, 2e-3, 1e-5, "row statistics")
+
+
+@pytest.mark.parametrize("m,k,n,splits", [(4096, 320, 640, 1), (256, 1280, 2560, 2), (64, 1280, 1280, 4)])
+def test_linear_layernorm_folded(cuda, m, k, n, splits):
+    """y = LayerNorm(x) W^T + b computed as rstd (x W'^T - mean colsum) + bias' from the producer's row statistics."""
+    ops = _ops()
+    x = (_rand((1, 1, m, k), cuda, 1) * 1.5 + 0.3).to(torch.float16)     # non-zero mean
+    w = _rand((n, k), cuda, 2, 1.0 / math.sqrt(k)).to(torch.float16)
+    gamma = (1.0 + 0.1 * _rand((k,), cuda, 3)).float()
+    beta = (0.1 * _rand((k,), cuda, 4)).float()
+    bias = _rand((n,), cuda, 5).float()
+    wp, colsum, bprime = _ln_fold_operands(w, gamma, beta, bias)
+    xf = x.reshape(m, k).double()
+    st = torch.stack([xf.sum(1), (xf * xf).sum(1)], dim=1).mul(STAT_SCALE).round().to(torch.int64).contiguous()
+    out = torch.full((1, 1, m, n), float("nan"), dtype=torch.float16, device=cuda)
+    ops.igemm([(x, 1)], wp, out, colbias=bprime.reshape(1, n).contiguous(), splits=splits, rowstat_in=st, colsum=colsum, ln_c=k)
+    ln = F.layer_norm(x.reshape(m, k).float(), (k,), gamma, beta, 1e-5)
+    ref = ln @ w.float().t() + bias
+    assert_close(out.reshape(m, n), ref, 6e-3, 4e-3, f"LN-folded linear m={m} k={k} n={n}")
+
+
+def test_fused_qkv_projection_with_transposed_v(cuda):
+    """One GEMM over [Wq | Wk | Wv] with LayerNorm folded: q/k columns row-major, the V block stored as V^T [C][tokens]
+    (the K-major operand of the attention P.V MMA), replacing a separate swapped-operand GEMM launch."""
+    ops = _ops()
+    m, c = 4096, 320
+    x = (_rand((1, 1, m, c), cuda, 1) + 0.2).to(torch.float16)
+    wq, wk, wv = (_rand((c, c), cuda, s, 1.0 / math.sqrt(c)).to(torch.float16) for s in (2, 3, 4))
+    gamma = (1.0 + 0.1 * _rand((c,), cuda, 5)).float()
+    beta = (0.1 * _rand((c,), cuda, 6)).float()
+    w = torch.cat([wq, wk, wv]).contiguous()
+    wp, colsum, bprime = _ln_fold_operands(w, gamma, beta, None)
+    xf = x.reshape(m, c).double()
+    st = torch.stack([xf.sum(1), (xf * xf).sum(1)], dim=1).mul(STAT_SCALE).round().to(torch.int64).contiguous()
+    qk = torch.full((1, 1, m, 2 * c), float("nan"), dtype=torch.float16, device=cuda)
+    vt = torch.full((c, m), float("nan"), dtype=torch.float16, device=cuda)
+    ops.igemm([(x, 1)], wp, qk, colbias=bprime.reshape(1, -1).contiguous(), n_valid=3 * c, rowstat_in=st, colsum=colsum, ln_c=c,
+              out2=vt, col2=2 * c, bn=160)
+    ln = F.layer_norm(x.reshape(m, c).float(), (c,), gamma, beta, 1e-5)
+    assert_close(qk.reshape(m, 2 * c), ln @ torch.cat([wq, wk]).float().t(), 6e-3, 4e-3, "q | k")
+    assert_close(vt, (ln @ wv.float().t()).t(), 6e-3, 4e-3, "V^T")
+
+
+def test_geglu_layernorm_folded(cuda):
+    ops = _ops()
+    m, k, inner = 1024, 320, 1280
+    x = (_rand((1, 1, m, k), cuda, 1) + 0.25).to(torch.float16)
+    w = _rand((2 * inner, k), cuda, 2, 1.0 / math.sqrt(k)).to(torch.float16)
+    b = _rand((2 * inner,), cuda, 3).float()
+    gamma = (1.0 + 0.1 * _rand((k,), cuda, 4)).float()
+    beta = (0.1 * _rand((k,), cuda, 5)).float()
+    half = 64
+    idx = []
+    for t in range(inner // half):
+        idx += list(range(t * half, (t + 1) * half))
+        idx += list(range(inner + t * half, inner + (t + 1) * half))
+    idx = torch.tensor(idx, device=cuda)
+    wp, colsum, bprime = _ln_fold_operands(w[idx].contiguous(), gamma, beta, b[idx])
+    xf = x.reshape(m, k).double()
+    st = torch.stack([xf.sum(1), (xf * xf).sum(1)], dim=1).mul(STAT_SCALE).round().to(torch.int64).contiguous()
+    out = torch.empty((1, 1, m, inner), dtype=torch.float16, device=cuda)
+    ops.igemm([(x, 1)], wp, out, colbias=bprime.reshape(1, -1).contiguous(), geglu=True, bn=128, n_valid=inner,
+              rowstat_in=st, colsum=colsum, ln_c=k)
+    proj = F.layer_norm(x.reshape(m, k).float(), (k,), gamma, beta, 1e-5) @ w.float().t() + b
+    ref = proj[:, :inner] * F.gelu(proj[:, inner:])
+    assert_close(out.reshape(m, inner), ref, 8e-3, 5e-3, "LN-folded GEGLU")
