@@ -11,6 +11,7 @@
 
 #include <functional>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -199,20 +200,38 @@ int igemm_autotile(IgemmDesc d, bool allow_swap, IgemmPlan* plan_out) {
     return 0;
 }
 
-struct b2sd_engine {
-    b2sd_config cfg{};
-    int lh = 0, lw = 0;  // latent extents
+// Parameters and everything derived from them (kernel-native packed layouts, fused fp32 vectors).  Read-only on the frame
+// path, so several engines ("lanes", b2sd_create_lane) share one store: one copy of the 1.7 GB UNet in HBM however many
+// frames are in flight.
+struct WeightStore {
     std::map<std::string, Raw> raw;
-    Arena weights{256u << 20};   // packed parameters + the raw ones kernels read directly (live for the engine's lifetime)
+    Arena weights{256u << 20};   // packed parameters + the raw ones kernels read directly (live for the store's lifetime)
     Arena raw_only{256u << 20};  // raw parameters that only feed the packing kernels: released after the first prepare
     bool raw_released = false;
     bool imported = false;       // parameters came from a packed blob (b2sd_import_packed)
-    Arena state{16u << 20};      // stream state + small persistent vectors
-    Arena prog{512u << 20};      // activations / per-program buffers (reset at prepare)
     std::map<std::string, __half*> packed;   // cache of packed weight matrices
     std::map<std::string, float*> fvec;      // cache of fp32 vectors
     std::map<std::string, size_t> packed_bytes, fvec_bytes;   // their sizes (b2sd_export_packed)
-    std::map<std::string, int*> perms;
+};
+
+struct b2sd_engine {
+    b2sd_config cfg{};
+    int lh = 0, lw = 0;  // latent extents
+    std::shared_ptr<WeightStore> ws;
+    std::map<std::string, Raw>& raw;
+    Arena& weights;
+    Arena& raw_only;
+    bool& raw_released;
+    bool& imported;
+    std::map<std::string, __half*>& packed;
+    std::map<std::string, float*>& fvec;
+    std::map<std::string, size_t>& packed_bytes;
+    std::map<std::string, size_t>& fvec_bytes;
+    Arena state{16u << 20};      // stream state + small persistent vectors
+    Arena prog{512u << 20};      // activations / per-program buffers (reset at prepare)
+    explicit b2sd_engine(std::shared_ptr<WeightStore> s)
+        : ws(std::move(s)), raw(ws->raw), weights(ws->weights), raw_only(ws->raw_only), raw_released(ws->raw_released),
+          imported(ws->imported), packed(ws->packed), fvec(ws->fvec), packed_bytes(ws->packed_bytes), fvec_bytes(ws->fvec_bytes) {}
 
     // persistent stream state (StreamDiffusion attributes)
     Act x_in;             // UNet input batch: slot 0 = fresh x_t, slots 1.. = x_t_latent_buffer
@@ -1054,7 +1073,28 @@ int b2sd_engine::build_program(cudaStream_t s) {
 // ================================================================================================
 extern "C" {
 
-int b2sd_create(const b2sd_config* cfg, b2sd_handle* out) {
+static int create_engine(const b2sd_config* cfg, std::shared_ptr<WeightStore> store, b2sd_handle* out);
+
+int b2sd_create(const b2sd_config* cfg, b2sd_handle* out) { return create_engine(cfg, std::make_shared<WeightStore>(), out); }
+
+/* A second engine over the SAME parameters (shared weight store): its own activations, stream state and CUDA graph, so two
+ * frames can be in flight on two CUDA streams.  cfg may differ from the parent's in batch / size only. */
+int b2sd_create_lane(b2sd_handle parent, const b2sd_config* cfg, b2sd_handle* out) {
+    if (!parent) {
+        b2_set_error("b2sd_create_lane: null parent");
+        return -1;
+    }
+    b2sd_config c = cfg ? *cfg : parent->cfg;
+    for (int i = 0; i < 4; ++i)
+        if (c.block_out_channels[i] != parent->cfg.block_out_channels[i] || c.heads[i] != parent->cfg.heads[i] ||
+            c.down_attn[i] != parent->cfg.down_attn[i]) {
+            b2_set_error("b2sd_create_lane: the lane's architecture differs from its parent's");
+            return -1;
+        }
+    return create_engine(&c, parent->ws, out);
+}
+
+static int create_engine(const b2sd_config* cfg, std::shared_ptr<WeightStore> store, b2sd_handle* out) {
     if (!cfg || !out) {
         b2_set_error("b2sd_create: null argument");
         return -1;
@@ -1085,7 +1125,7 @@ int b2sd_create(const b2sd_config* cfg, b2sd_handle* out) {
         return -1;
     }
     if (igemm_init() || attn_init() || tconv_init()) return -1;
-    b2sd_engine* e = new b2sd_engine();
+    b2sd_engine* e = new b2sd_engine(std::move(store));
     e->cfg = *cfg;
     e->lh = cfg->height / 8;
     e->lw = cfg->width / 8;

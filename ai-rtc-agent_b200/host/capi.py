@@ -102,6 +102,7 @@ def lib() -> C.CDLL:
         _lib.b2sd_op_post_u8.argtypes = [vp, ci, vp, ci, ci, ci, vp]
         _lib.b2sd_create.argtypes = [C.POINTER(EngineConfig), C.POINTER(vp)]
         _lib.b2sd_destroy.argtypes = [vp]
+        _lib.b2sd_create_lane.argtypes = [vp, C.POINTER(EngineConfig), C.POINTER(vp)]
         _lib.b2sd_load_tensor.argtypes = [vp, C.c_char_p, vp, ci, C.POINTER(i64), ci]
         _lib.b2sd_prepare.argtypes = [vp, vp, vp, vp, vp, vp]
         _lib.b2sd_export_packed.argtypes = [vp, C.c_char_p]
@@ -116,7 +117,7 @@ def lib() -> C.CDLL:
         _lib.b2sd_profile.restype = C.c_int
         _lib.b2sd_profile_kind.argtypes = [vp, C.c_char_p, ci, C.POINTER(C.c_double), C.POINTER(ci), C.POINTER(C.c_double), vp]
         _lib.b2sd_profile_kind.restype = C.c_int
-        for name in ("create", "destroy", "load_tensor", "prepare", "export_packed", "import_packed", "set_prompt_embeds", "set_timesteps", "step",
+        for name in ("create", "create_lane", "destroy", "load_tensor", "prepare", "export_packed", "import_packed", "set_prompt_embeds", "set_timesteps", "step",
                      "step_ex", "get_tensor", "launches_per_step"):
             getattr(_lib, "b2sd_" + name).restype = C.c_int
         for name in ("attention", "groupnorm", "layernorm", "upsample2x", "smallconv", "lcm_step", "post_u8"):

@@ -53,7 +53,10 @@ def _as_torch_u8_nhwc(frame, device) -> torch.Tensor:
 
 class StreamDiffusionPipeline:
     def __init__(self, model_id: str, t_index_list: Optional[List[int]] = None, width: int = 512, height: int = 512,
-                 prompt: str = DEFAULT_PROMPT):
+                 prompt: str = DEFAULT_PROMPT, lanes: Optional[int] = None):
+        """lanes: frames in flight for enqueue().  With a 1-step stream batch (SD-Turbo) consecutive frames are independent, so
+        two lanes (default there; $B200SD_LANES overrides) process frame n+1 while frame n is still on the GPU, bit-identical
+        to sequential processing.  With T > 1 the stream batch carries state from frame to frame: always one lane."""
         self.prompt = prompt
         self.t_index_list = list(t_index_list) if t_index_list is not None else DEFAULT_T_INDEX_LIST
         self.device = "cuda"
@@ -75,12 +78,46 @@ class StreamDiffusionPipeline:
         )
         self.model.prepare(prompt=self.prompt, num_inference_steps=DEFAULT_NUM_INFERENCE_STEPS,
                            guidance_scale=DEFAULT_GUIDANCE_SCALE)
+        if lanes is None:
+            lanes = int(os.getenv("B200SD_LANES", "0")) or (2 if len(self.t_index_list) == 1 else 1)
+        if len(self.t_index_list) > 1:
+            lanes = 1          # x_t_latent_buffer chains frame n+1 to frame n
+        sd = self.model.stream
+        self._engines = [sd] + [sd.add_lane() for _ in range(max(1, lanes) - 1)]
+        # one lane: frames run on the caller's stream, exactly as before.  Several lanes: every lane has its own stream (a lane on
+        # the caller's stream would order the other lanes' "input ready" events behind its frames and serialise them)
+        self._lane_streams = [None] if len(self._engines) == 1 else [torch.cuda.Stream(sd.device) for _ in self._engines]
+        self._lane_done = [None] * len(self._engines)     # completion event of the last frame given to each lane
+        self._next_lane = 0
+
+    @property
+    def lanes(self) -> int:
+        return len(self._engines)
+
+    def _quiesce(self):
+        """Every lane finishes its queued frames before a prompt / timestep update touches the shared schedule."""
+        cur = torch.cuda.current_stream(self.model.stream.device)
+        for ev in self._lane_done:
+            if ev is not None:
+                cur.wait_event(ev)
+        return cur
+
+    def _release(self, cur):
+        done = torch.cuda.Event()
+        done.record(cur)
+        for st in self._lane_streams:
+            if st is not None:
+                st.wait_event(done)
 
     def update_prompt(self, prompt: str):
+        cur = self._quiesce()
         self.model.stream.update_prompt(prompt)
+        self._release(cur)
 
     def update_t_index_list(self, t_index_list: List[int]):
+        cur = self._quiesce()
         self.model.update_t_index_list(t_index_list)
+        self._release(cur)
 
     # ---- reference-shaped stages ----------------------------------------------------------------------
     def preprocess(self, frame) -> torch.Tensor:
@@ -103,7 +140,11 @@ class StreamDiffusionPipeline:
     def __call__(self, frame):
         """lib/pipeline.py:76-96, blocking semantics preserved: the result is complete when the call returns only in the
         software-encode branch (`.cpu()`); with NVENC set the CUDA tensor is returned stream-ordered, like the reference."""
-        return self.enqueue(frame).result(wait=not os.getenv("NVENC"))
+        ticket = self.enqueue(frame)
+        if os.getenv("NVENC"):
+            ticket.wait(torch.cuda.current_stream(self.model.stream.device))   # stream-ordered result, whichever lane ran it
+            return ticket.result(wait=False)
+        return ticket.result()
 
     # ---- non-blocking entry (SURVEY.md 8f-2): everything is queued on CUDA streams and a ticket comes back at once ------
     def enqueue(self, frame) -> "FrameTicket":
@@ -114,7 +155,15 @@ class StreamDiffusionPipeline:
         if not _is_gpu_frame(frame) and not _is_video_frame(frame):
             raise Exception("invalid frame type")
         dev = self.model.stream.device
-        compute = torch.cuda.current_stream(dev)
+        caller = torch.cuda.current_stream(dev)
+        lane = self._next_lane
+        self._next_lane = (lane + 1) % len(self._engines)
+        engine = self._engines[lane]
+        compute = self._lane_streams[lane] or caller
+        if compute is not caller:
+            ready = torch.cuda.Event()
+            ready.record(caller)          # whatever produced the frame on the caller's stream
+            compute.wait_event(ready)
         if _is_video_frame(frame):
             self._ensure_staging(dev)
             slot = self._slot
@@ -134,12 +183,18 @@ class StreamDiffusionPipeline:
         else:
             slot = None
             rgb = _as_torch_u8_nhwc(frame, self.device)
-        post_output = self.model.stream.step_u8(rgb)
+            if compute is not caller:
+                rgb.record_stream(compute)
+        with torch.cuda.stream(compute):
+            post_output = engine.step_u8(rgb)
+        if compute is not caller:
+            post_output.record_stream(caller)
         if slot is not None:
             self._slot_free[slot].record(compute)
         done = torch.cuda.Event()
         if os.getenv("NVENC"):
             done.record(compute)
+            self._lane_done[lane] = done
             return FrameTicket(post_output, done, None, None)
         # software-encode branch (lib/pipeline.py:83-94): hand back an av.VideoFrame with the input's timing
         assert _is_video_frame(frame)
@@ -152,6 +207,7 @@ class StreamDiffusionPipeline:
             host_out.copy_(post_output, non_blocking=True)
             post_output.record_stream(self._copy_stream)
             done.record(self._copy_stream)
+        self._lane_done[lane] = done
         return FrameTicket(post_output, done, host_out, frame)
 
     def _ensure_staging(self, dev) -> None:
@@ -172,6 +228,10 @@ class FrameTicket:
     def done(self) -> bool:
         """True once every GPU operation of this frame (and the download, if any) has finished; never blocks."""
         return self._done.query()
+
+    def wait(self, stream) -> None:
+        """Make `stream` wait for this frame (no host synchronisation): later work on it sees the finished tensor."""
+        stream.wait_event(self._done)
 
     def result(self, wait: bool = True):
         """The (1,3,H,W) u8 CUDA tensor (NVENC set) or an av.VideoFrame carrying the input's pts/time_base."""

@@ -74,7 +74,7 @@ class StreamDiffusion:
                  torch_dtype: torch.dtype = torch.float16, width: int = 512, height: int = 512,
                  do_add_noise: bool = True, use_denoising_batch: bool = True, frame_buffer_size: int = 1,
                  cfg_type: str = "self", device: str = "cuda", use_cuda_graph: bool = True,
-                 packed_blob: Optional[str] = None):
+                 packed_blob: Optional[str] = None, parent: Optional["StreamDiffusion"] = None):
         if frame_buffer_size != 1:
             raise NotImplementedError("frame_buffer_size > 1 is not on the reference's path (lib/pipeline.py:28)")
         if not use_denoising_batch:
@@ -125,6 +125,15 @@ class StreamDiffusion:
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         torch.cuda.set_device(self.device)
+        self._ctor = dict(torch_dtype=torch_dtype, width=width, height=height, do_add_noise=do_add_noise,
+                          use_denoising_batch=use_denoising_batch, frame_buffer_size=frame_buffer_size, cfg_type=cfg_type,
+                          device=device, use_cuda_graph=use_cuda_graph)
+        self.lanes: List["StreamDiffusion"] = []     # extra engines over this one's weights (add_lane)
+        self._parent = parent
+        if parent is not None:
+            # a lane: shares the parent's weights in HBM, owns its activations / stream state / CUDA graph
+            capi.check(self._lib.b2sd_create_lane(parent._handle, C.byref(cfg), C.byref(self._handle)), "b2sd_create_lane")
+            return
         capi.check(self._lib.b2sd_create(C.byref(cfg), C.byref(self._handle)), "b2sd_create")
         if packed_blob is not None:
             # kernel-native weights written by export_packed() / `python -m ai_rtc_agent_b200.pack`: no state dicts, no repacking
@@ -190,6 +199,14 @@ class StreamDiffusion:
         self.c_out = f16([s[1] for s in scal]).view(T, 1, 1, 1)
         self.alpha_prod_t_sqrt = torch.stack([ac[t].sqrt() for t in self.sub_timesteps]).to(self.dtype).view(T, 1, 1, 1)
         self.beta_prod_t_sqrt = torch.stack([(1 - ac[t]).sqrt() for t in self.sub_timesteps]).to(self.dtype).view(T, 1, 1, 1)
+        self._engine_prepare()
+        for lane in self.lanes:
+            lane._prepare_like(self)
+
+    _SCHEDULE_ATTRS = ("generator", "guidance_scale", "delta", "prompt_embeds", "timesteps", "sub_timesteps", "sub_timesteps_tensor",
+                       "init_noise", "stock_noise", "c_skip", "c_out", "alpha_prod_t_sqrt", "beta_prod_t_sqrt")
+
+    def _engine_prepare(self) -> None:
         coef = torch.stack([self.alpha_prod_t_sqrt.flatten(), self.beta_prod_t_sqrt.flatten(),
                             self.c_skip.flatten(), self.c_out.flatten()]).float().contiguous()
         tsteps = torch.tensor(self.sub_timesteps, dtype=torch.float32)
@@ -198,6 +215,22 @@ class StreamDiffusion:
         capi.check(self._lib.b2sd_prepare(self._handle, emb.data_ptr(), tsteps.data_ptr(), coef.data_ptr(),
                                           noise.data_ptr(), self._stream()), "b2sd_prepare")
         self._prepared = True
+
+    def _prepare_like(self, other: "StreamDiffusion") -> None:
+        for name in self._SCHEDULE_ATTRS:
+            setattr(self, name, getattr(other, name))
+        self.t_list = list(other.t_list)
+        self._engine_prepare()
+
+    def add_lane(self) -> "StreamDiffusion":
+        """Another engine over the same weights, prepared identically (same prompt embedding, schedule and seed-2 noise):
+        frames may be alternated between this engine and its lanes on different CUDA streams.  Later prepare() /
+        update_prompt() / timestep updates on this object reach every lane."""
+        self._check()
+        lane = StreamDiffusion(self.arch, {}, {}, self.t_list, self.prompt_encoder, parent=self, **self._ctor)
+        lane._prepare_like(self)
+        self.lanes.append(lane)
+        return lane
 
     def _encode(self, prompt: str) -> torch.Tensor:
         e = self.prompt_encoder(prompt)
@@ -211,7 +244,9 @@ class StreamDiffusion:
     def update_prompt(self, prompt: str) -> None:
         self.prompt_embeds = self._encode(prompt).repeat(self.batch_size, 1, 1)
         emb = self.prompt_embeds[0].cpu().contiguous()
-        capi.check(self._lib.b2sd_set_prompt_embeds(self._handle, emb.data_ptr(), self._stream()), "b2sd_set_prompt_embeds")
+        for eng in [self] + self.lanes:
+            eng.prompt_embeds = self.prompt_embeds
+            capi.check(self._lib.b2sd_set_prompt_embeds(eng._handle, emb.data_ptr(), self._stream()), "b2sd_set_prompt_embeds")
 
     def sync_timesteps(self) -> None:
         """Push self.sub_timesteps to the engine (called after lib/wrapper.py:389-407 style updates).  As in the
@@ -220,7 +255,9 @@ class StreamDiffusion:
         if t.numel() != self.batch_size:
             raise ValueError(f"t_index_list length {t.numel()} != stream batch {self.batch_size} (static batch, as the "
                              "reference's TensorRT engines)")
-        capi.check(self._lib.b2sd_set_timesteps(self._handle, t.data_ptr(), self._stream()), "b2sd_set_timesteps")
+        for eng in [self] + self.lanes:
+            eng.t_list, eng.sub_timesteps, eng.sub_timesteps_tensor = self.t_list, self.sub_timesteps, self.sub_timesteps_tensor
+            capi.check(self._lib.b2sd_set_timesteps(eng._handle, t.data_ptr(), self._stream()), "b2sd_set_timesteps")
 
     # ---- per frame ---------------------------------------------------------------------------------
     def _check(self):

@@ -161,6 +161,14 @@ typedef struct {
 
 int b2sd_create(const b2sd_config* cfg, b2sd_handle* out);
 int b2sd_destroy(b2sd_handle h);
+/* A "lane": a second engine over the SAME parameters as `parent` (one copy of the weights in HBM), with its own activations,
+ * stream state and CUDA graph, so that several frames can be in flight on different CUDA streams.  cfg = NULL copies the
+ * parent's; otherwise only batch / height / width may differ.  Prepare it like any engine (after the parent's first
+ * b2sd_prepare, which lays the weights out).  With a 1-step stream batch (SD-Turbo) consecutive frames of ONE video stream are
+ * independent, so alternating them over two lanes overlaps frame n+1 with frame n and yields bit-identical output; lanes are
+ * also how several independent video streams share one GPU.  (The reference serialises everything behind a per-frame
+ * torch.cuda.synchronize()) */
+int b2sd_create_lane(b2sd_handle parent, const b2sd_config* cfg, b2sd_handle* out);
 
 /* Weights under diffusers state-dict names: UNet keys as-is ("down_blocks.0.resnets.0.conv1.weight"),
  * TAESD keys prefixed "vae." ("vae.encoder.layers.0.weight").  ptr may be host or device memory.

