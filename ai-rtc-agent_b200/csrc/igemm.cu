@@ -629,7 +629,7 @@ static int plan_swap(const IgemmDesc& d, IgemmPlan* plan) {
     const size_t stage_bytes = (size_t)IG_BM * IG_BK * 2 + (size_t)BN * IG_BK * 2;
     // swapped launches are small grids (<= ~1 CTA per SM): give the ring most of the shared memory
     static const char* sw_stage_env = getenv("B2_SWAP_STAGE_KB");
-    int stages = (int)(((size_t)(sw_stage_env ? atoi(sw_stage_env) : 200) * 1024) / stage_bytes);
+    int stages = (int)(((size_t)(sw_stage_env ? atoi(sw_stage_env) : (d.ring_kb > 0 ? d.ring_kb : 200)) * 1024) / stage_bytes);
     if (stages < 2) stages = 2;
     if (stages > IG_MAX_STAGES) stages = IG_MAX_STAGES;
     if (stages > p.kb_per_split) stages = p.kb_per_split < 2 ? 2 : p.kb_per_split;
@@ -782,7 +782,8 @@ int igemm_plan(const IgemmDesc& d, IgemmPlan* plan) {
     const long total_ctas = will_persist ? persist_ctas : all_tiles * splits;
     static const char* stage_env = getenv("B2_STAGE_KB");
     // <= 1 CTA per SM anyway: take (nearly) all the shared memory for the ring, the mainloop is TMA-latency bound
-    const size_t ring_budget = stage_env ? (size_t)atoi(stage_env) * 1024 : (size_t)((total_ctas <= 148 ? 200 : 100) * 1024);
+    const size_t ring_budget = stage_env ? (size_t)atoi(stage_env) * 1024
+                                         : (d.ring_kb > 0 ? (size_t)d.ring_kb * 1024 : (size_t)((total_ctas <= 148 ? 200 : 100) * 1024));
     int stages = (int)(ring_budget / stage_bytes);
     if (stages < 2) stages = 2;
     if (stages > IG_MAX_STAGES) stages = IG_MAX_STAGES;

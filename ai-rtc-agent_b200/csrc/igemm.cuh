@@ -101,6 +101,8 @@ struct IgemmDesc {
     int BN;           // 0 = auto
     int swap;         // 1 = swapped orientation: D^T = W . X^T, BN pixels (64/128/256) on the N side, transposed store
     int splits;       // 0/1 = none
+    int ring_kb;      // operand ring budget in KB, 0 = auto (200 when the launch has <= 1 CTA per SM, else 100)
+    int max_splits;   // cap of the split-K factor chosen by igemm_autotile, 0 = 8
     unsigned long long* dbg_ts;  // optional per-CTA timeline (8 stamps per CTA)
     float* partial;   // unused since split-K moved into a cluster (kept for ABI stability; op-level entry: debug timeline)
     int* tile_counters;  // unused (ABI stability)

@@ -113,6 +113,8 @@ def lib() -> C.CDLL:
         _lib.b2sd_step_ex.argtypes = [vp, vp, ci, ci, ci, vp, ci, vp]
         _lib.b2sd_get_tensor.argtypes = [vp, C.c_char_p, vp, i64, C.POINTER(i64), C.POINTER(ci), vp]
         _lib.b2sd_launches_per_step.argtypes = [vp]
+        _lib.b2sd_set_concurrency.argtypes = [vp, ci]
+        _lib.b2sd_set_concurrency.restype = C.c_int
         _lib.b2sd_profile.argtypes = [vp, vp, ci, ci, vp, ci, C.c_char_p, i64, vp]
         _lib.b2sd_profile.restype = C.c_int
         _lib.b2sd_profile_kind.argtypes = [vp, C.c_char_p, ci, C.POINTER(C.c_double), C.POINTER(ci), C.POINTER(C.c_double), vp]

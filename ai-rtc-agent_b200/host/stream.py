@@ -142,6 +142,12 @@ class StreamDiffusion:
             self._load("", unet_sd)
             self._load("vae.", vae_sd)
 
+    def set_concurrency(self, frames_in_flight: int) -> None:
+        """Tell the engine how many frames will be in flight on this GPU (before prepare()): > 1 selects the throughput
+        launch policy (b2sd_set_concurrency)."""
+        capi.check(self._lib.b2sd_set_concurrency(self._handle, int(frames_in_flight)), "b2sd_set_concurrency")
+        self._prepared = False
+
     def export_packed(self, path: str) -> None:
         """Write the packed-weight blob (after prepare()); the engine-file cache of lib/wrapper.py:593-597, 896-910."""
         self._check()

@@ -230,6 +230,10 @@ int b2sd_profile_kind(b2sd_handle h, const char* kind, int iters, double* ms_per
                       void* stream);
 /* number of kernel launches (graph nodes) in one b2sd_step */
 int b2sd_launches_per_step(b2sd_handle h);
+/* How many frames will be in flight on this GPU (lanes / independent streams).  1 (default): launch policy tuned for the
+ * latency of a single frame; > 1: policy tuned for throughput (smaller operand rings so CTAs of different frames share an
+ * SM).  Takes effect at the next b2sd_prepare. */
+int b2sd_set_concurrency(b2sd_handle h, int frames_in_flight);
 
 #ifdef __cplusplus
 }
