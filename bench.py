@@ -447,7 +447,31 @@ def main_gpu(args):
     # dominant kernel: its launches alone, replayed from their own CUDA graph (same order, buffers, PDL edges and weight
     # streaming as inside the frame graph) -> average launch duration without the host-side gaps of the eager replay
     ig = stream.profile_kind("igemm", iters=20)
-    ig_tflops = ig["flops"] / (ig["ms"] * 1e-3) / 1e12
+    ig_tflops_seq = ig["flops"] / (ig["ms"] * 1e-3) / 1e12
+
+    def concurrent_kind(kind, iters=60):
+        """The launches of one class of ALL lanes replayed at the same time (one host thread + CUDA stream per lane, like the
+        frames in flight of the timed region): aggregate algorithmic FLOP/s of that kernel under the conditions it really runs in."""
+        import threading
+        res = [None] * lanes
+        gate = threading.Barrier(lanes)
+
+        def work(k):
+            torch.cuda.set_device(dev)
+            with torch.cuda.stream(torch.cuda.Stream(dev)):
+                gate.wait()
+                res[k] = pipe._engines[k].profile_kind(kind, iters=iters)
+
+        th = [threading.Thread(target=work, args=(k,)) for k in range(lanes)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        ms = sum(r["ms"] for r in res) / lanes
+        return {"ms": ms, "flops": sum(r["flops"] for r in res), "launches": res[0]["launches"]}
+
+    igc = concurrent_kind("igemm") if lanes > 1 else ig
+    ig_tflops = igc["flops"] / (igc["ms"] * 1e-3) / 1e12
     kinds = {}
     for kind in ("tconv", "attn", "groupnorm", "layernorm"):
         try:
@@ -470,10 +494,15 @@ def main_gpu(args):
         "frac": ig_tflops / peaks["bf16_tflops_sustained"], "traffic": traffic,
         "peak_source": peak_src + ", sustained figure (kernel timed inside a long step)",
         "traffic_note": traffic_note,
-        "kernel_share_of_step": ig["ms"] / step_ms, "kernel_launches_per_step": ig["launches"],
-        "kernel_ms_per_step": ig["ms"], "kernel_avg_launch_us": 1e3 * ig["ms"] / max(ig["launches"], 1),
-        "kernel_timing": "CUDA events around a graph holding only the igemm launches of one frame, 20 replays",
+        "kernel_share_of_step": (igc["ms"] / lanes) / step_ms, "kernel_launches_per_step": ig["launches"],
+        "kernel_ms_per_step": igc["ms"] / lanes, "kernel_avg_launch_us": 1e3 * (igc["ms"] / lanes) / max(ig["launches"], 1),
+        "kernel_timing": f"CUDA events around graphs holding only the igemm launches of one frame; {lanes} such graphs (one per lane, as "
+                         "many frames as the timed region keeps in flight) replayed concurrently on their own streams, 60 replays each: "
+                         "achieved = their summed algorithmic FLOPs / the mean replay time; kernel_ms_per_step = that time / lanes",
         "kernel_algorithmic_gflop_per_step": ig["flops"] / 1e9,
+        "one_frame_at_a_time": {"achieved": ig_tflops_seq, "frac": ig_tflops_seq / peaks["bf16_tflops_sustained"],
+                                "kernel_ms_per_step": ig["ms"], "kernel_avg_launch_us": 1e3 * ig["ms"] / max(ig["launches"], 1),
+                                "note": "the same launches of ONE frame alone on the GPU (a dependent chain; round 1's figure)"},
         "step_achieved": step_tflops, "step_frac": step_tflops / peaks["bf16_tflops_sustained"],
         "step_algorithmic_gflop": GFLOP_PER_FRAME,
         "other_kernels_in_graph": kinds,

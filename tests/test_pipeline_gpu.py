@@ -174,11 +174,18 @@ def test_two_lanes_equal_sequential_processing(cuda, monkeypatch):
     a prompt / timestep update issued while frames are in flight."""
     from oracle import pipeline as opipe
     from oracle import weights as ow
-    one, orc = _pipeline("tiny-turbo", [32], 128, monkeypatch, lanes=1)
+    # `one`: the same two-lane engine configuration driven one frame at a time through the blocking call (each call waits
+    # for its frame), `two`: frames submitted back to back.  (A lanes=1 pipeline plans its launches for latency -- other
+    # split-K factors, hence other fp32 summation orders -- and agrees to within 1 LSB, checked below.)
+    one, orc = _pipeline("tiny-turbo", [32], 128, monkeypatch, lanes=2)
     two, _ = _pipeline("tiny-turbo", [32], 128, monkeypatch, lanes=2)
-    assert one.lanes == 1 and two.lanes == 2
+    single, _ = _pipeline("tiny-turbo", [32], 128, monkeypatch, lanes=1)
+    assert one.lanes == 2 and two.lanes == 2 and single.lanes == 1
     frames = [ow.make_frame(128, 128, seed=80 + i).cuda() for i in range(10)]
     want = [one(f).cpu() for f in frames[:8]]
+    for f, w in zip(frames[:3], want):
+        d = (single(f).cpu().int() - w.int()).abs()
+        assert d.max().item() <= 1, "latency-policy and throughput-policy programs differ only by fp32 summation order"
     tickets = [two.enqueue(f) for f in frames[:6]]
     for i, t in enumerate(tickets):
         assert torch.equal(t.result().cpu(), want[i]), f"frame {i}"
