@@ -2,6 +2,7 @@
 #include "../../include/b200sd.h"
 
 #include "attention.cuh"
+#include "codec.cuh"
 #include "elementwise.cuh"
 #include "igemm.cuh"
 #include "tconv.cuh"
@@ -116,6 +117,16 @@ int b2sd_groupnorm_plan_dry(int ca, int cb, int groups, int hw, int* cluster, in
 uint64_t b2sd_igemm_partial_floats(int splits, int64_t rows_total, int n_valid) {
     return igemm_partial_floats(splits, rows_total, n_valid);
 }
+
+int b2sd_op_nv12_to_rgb(const void* y, int y_pitch, const void* uv, int uv_pitch, void* rgb_nhwc, int h, int w, int flags, void* stream) {
+    return nv12_to_rgb_u8_launch(static_cast<const uint8_t*>(y), y_pitch, static_cast<const uint8_t*>(uv), uv_pitch,
+                                 static_cast<uint8_t*>(rgb_nhwc), h, w, flags, reinterpret_cast<cudaStream_t>(stream));
+}
+int b2sd_op_rgb_to_nv12(const void* rgb_nchw, void* y, int y_pitch, void* uv, int uv_pitch, int h, int w, int flags, void* stream) {
+    return rgb_u8_to_nv12_launch(static_cast<const uint8_t*>(rgb_nchw), static_cast<uint8_t*>(y), y_pitch, static_cast<uint8_t*>(uv),
+                                 uv_pitch, h, w, flags, reinterpret_cast<cudaStream_t>(stream));
+}
+int b2sd_codec_probe(void) { return codec_probe(); }
 
 int b2sd_op_attention(const b2sd_attn_desc* d, void* stream) {
     AttnDesc a{};

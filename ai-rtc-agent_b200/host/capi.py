@@ -100,6 +100,9 @@ def lib() -> C.CDLL:
         _lib.b2sd_op_smallconv.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
         _lib.b2sd_op_lcm_step.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, vp]
         _lib.b2sd_op_post_u8.argtypes = [vp, ci, vp, ci, ci, ci, vp]
+        _lib.b2sd_op_nv12_to_rgb.argtypes = [vp, ci, vp, ci, vp, ci, ci, ci, vp]
+        _lib.b2sd_op_rgb_to_nv12.argtypes = [vp, vp, ci, vp, ci, ci, ci, ci, vp]
+        _lib.b2sd_codec_probe.restype = C.c_int
         _lib.b2sd_create.argtypes = [C.POINTER(EngineConfig), C.POINTER(vp)]
         _lib.b2sd_destroy.argtypes = [vp]
         _lib.b2sd_create_lane.argtypes = [vp, C.POINTER(EngineConfig), C.POINTER(vp)]
@@ -122,7 +125,7 @@ def lib() -> C.CDLL:
         for name in ("create", "create_lane", "destroy", "load_tensor", "prepare", "export_packed", "import_packed", "set_prompt_embeds", "set_timesteps", "step",
                      "step_ex", "get_tensor", "launches_per_step"):
             getattr(_lib, "b2sd_" + name).restype = C.c_int
-        for name in ("attention", "groupnorm", "layernorm", "upsample2x", "smallconv", "lcm_step", "post_u8"):
+        for name in ("attention", "groupnorm", "layernorm", "upsample2x", "smallconv", "lcm_step", "post_u8", "nv12_to_rgb", "rgb_to_nv12"):
             getattr(_lib, "b2sd_op_" + name).restype = C.c_int
     return _lib
 

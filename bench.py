@@ -306,12 +306,14 @@ def main_gpu(args):
     os.environ.setdefault("B200SD_SYNTHETIC_WEIGHTS", "1")
     world_env = int(os.getenv("WORLD_SIZE", "1"))
     nccl_glob = None
-    if world_env > 1:
-        # keep stdout to the single JSON line, but keep NCCL's own account of the job: INFO level into per-process files
-        # (a caller-provided NCCL_DEBUG / NCCL_DEBUG_FILE wins)
+    nccl_env = {k: v for k, v in os.environ.items() if k.startswith("NCCL_DEBUG")}
+    if world_env > 1 and "NCCL_DEBUG" not in os.environ:
+        # nobody asked for NCCL's log: keep stdout to the single JSON line, but still keep NCCL's own account of the job
+        # (INFO level into per-process files, summarised in the line's "nccl" field).  A caller-provided NCCL_DEBUG is left
+        # exactly as it is -- level and destination -- so a harness that reads NCCL's output from this process keeps seeing it.
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(ROOT, "gpurun_out", f"nccl_n{world_env}_%h_%p.log"))
+        os.environ["NCCL_DEBUG"] = "INFO"
+        os.environ["NCCL_DEBUG_FILE"] = os.path.join(ROOT, "gpurun_out", f"nccl_n{world_env}_%h_%p.log")
         nccl_glob = os.environ["NCCL_DEBUG_FILE"].replace("%h", "*").replace("%p", "*")
     os.environ["NVENC"] = "1"  # keep the output tensor in HBM (lib/pipeline.py:83,96)
     from ai_rtc_agent_b200.host import dist as bdist
@@ -541,8 +543,8 @@ def main_gpu(args):
         "roofline": roofline, "library_baseline": lib, "cpu_baseline": cpu, "clocks": clocks,
     }
     if world > 1:
-        line["nccl"] = dict(nccl_log_summary(nccl_glob) if nccl_glob else {}, world_size=world,
-                            backend=dist.get_backend(), collectives_per_step=0)
+        line["nccl"] = dict(nccl_log_summary(nccl_glob) if nccl_glob else {"log": "NCCL_DEBUG* set by the caller, left untouched"},
+                            caller_env=nccl_env, world_size=world, backend=dist.get_backend(), collectives_per_step=0)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

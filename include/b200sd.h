@@ -134,6 +134,14 @@ int b2sd_op_smallconv(const void* x, const void* w_oihw, const float* bias, void
 /* StreamDiffusion scheduler_step_batch + stream-batch buffer update (see elementwise.cuh) */
 int b2sd_op_lcm_step(void* x, const void* eps, const void* noise, const float* coef, void* out_latent, int T,
                      int hw, int do_add_noise, void* stream);
+/* Codec boundary (the reference's aiortc fork decodes with NVDEC / encodes with NVENC, requirements.txt:12-13,
+ * and exchanges RGB tensors in HBM with lib/pipeline.py:50-51,83,96).  NV12 surface (Y plane + interleaved UV plane, pitches in
+ * bytes) <-> the frame formats of b2sd_step: u8 NHWC RGB in, u8 NCHW RGB out.  flags: 0 = BT.709 limited range,
+ * B2SD_CSC_BT601, B2SD_CSC_FULL_RANGE.  b2sd_codec_probe: bit 0 = libnvcuvid loadable, bit 1 = libnvidia-encode loadable. */
+enum { B2SD_CSC_BT601 = 1, B2SD_CSC_FULL_RANGE = 2 };
+int b2sd_op_nv12_to_rgb(const void* y, int y_pitch, const void* uv, int uv_pitch, void* rgb_nhwc, int h, int w, int flags, void* stream);
+int b2sd_op_rgb_to_nv12(const void* rgb_nchw, void* y, int y_pitch, void* uv, int uv_pitch, int h, int w, int flags, void* stream);
+int b2sd_codec_probe(void);
 /* decoder tail + lib/pipeline.py:72-74 on the fp16 grid -> u8 NCHW */
 int b2sd_op_post_u8(const void* y_nhwc, int ldy, void* out_nchw_u8, int nb, int h, int w, void* stream);
 

@@ -282,3 +282,48 @@ def test_pack_cli_argument_parsing():
     assert pack.parse_lora(["a.safetensors:0.5", "/x/y.safetensors"]) == {"a.safetensors": 0.5, "/x/y.safetensors": 1.0}
     with pytest.raises(SystemExit):
         pack.parse_lora(["a.safetensors:fast"])
+
+
+def _write_tiny_clip(model_dir, hidden=64):
+    """text_encoder/ + tokenizer/ of a diffusers checkpoint (lib/wrapper.py:468-473 loads exactly these two sub-folders):
+    a 2-layer CLIPTextModel with random weights and a character-level BPE vocabulary, saved with save_pretrained."""
+    import json
+    from transformers import CLIPTextConfig, CLIPTextModel, CLIPTokenizer
+    vocab = {"<|startoftext|>": 0, "<|endoftext|>": 1}
+    for c in "abcdefghijklmnopqrstuvwxyz":
+        vocab[c] = len(vocab)
+    for c in "abcdefghijklmnopqrstuvwxyz":
+        vocab[c + "</w>"] = len(vocab)
+    tok_dir, te_dir = os.path.join(model_dir, "tokenizer"), os.path.join(model_dir, "text_encoder")
+    os.makedirs(tok_dir, exist_ok=True)
+    json.dump(vocab, open(os.path.join(tok_dir, "vocab.json"), "w"))
+    open(os.path.join(tok_dir, "merges.txt"), "w").write("#version: 0.2\n")
+    CLIPTokenizer(os.path.join(tok_dir, "vocab.json"), os.path.join(tok_dir, "merges.txt"), model_max_length=77).save_pretrained(tok_dir)
+    torch.manual_seed(3)
+    cfg = CLIPTextConfig(vocab_size=len(vocab), hidden_size=hidden, intermediate_size=2 * hidden, num_hidden_layers=2,
+                         num_attention_heads=2, max_position_embeddings=77, projection_dim=hidden, bos_token_id=0, eos_token_id=1,
+                         pad_token_id=1)
+    CLIPTextModel(cfg).save_pretrained(te_dir)
+
+
+def test_clip_prompt_encoder_from_a_checkpoint_directory(tmp_path):
+    """the text encoder on the update path (lib/wrapper.py:468-473, lib/pipeline.py:44-45) -- tokenizer +
+    CLIPTextModel from the checkpoint's sub-folders, (1,77,D) fp16 last_hidden_state, padded / truncated to 77 tokens."""
+    from transformers import CLIPTextModel, CLIPTokenizer
+    from ai_rtc_agent_b200.host.prompt import ClipPromptEncoder, make_prompt_encoder
+    d = str(tmp_path / "ckpt")
+    os.makedirs(d)
+    _write_tiny_clip(d, hidden=64)
+    enc = make_prompt_encoder(d, 64, "cpu")
+    assert isinstance(enc, ClipPromptEncoder)
+    a, b, a2 = enc("fireworks in the night sky"), enc("a cat"), enc("fireworks in the night sky")
+    assert a.shape == (1, 77, 64) and a.dtype == torch.float16
+    assert torch.equal(a, a2) and not torch.equal(a, b)
+    long_prompt = enc("word " * 200)          # truncation to model_max_length
+    assert long_prompt.shape == (1, 77, 64)
+    tok = CLIPTokenizer.from_pretrained(os.path.join(d, "tokenizer"))
+    ref = CLIPTextModel.from_pretrained(os.path.join(d, "text_encoder"))
+    ids = tok("a cat", padding="max_length", max_length=77, truncation=True, return_tensors="pt").input_ids
+    assert torch.allclose(b.float(), ref(ids)[0].float(), atol=2e-2)
+    with pytest.raises(ValueError, match="hidden size"):
+        make_prompt_encoder(d, 768, "cpu")    # encoder / UNet mismatch must not pass silently

@@ -210,3 +210,59 @@ def test_post_u8_truncation_semantics(cuda):
     den = (img / 2 + 0.5).clamp(0, 1)                   # fp16
     ref = (den * 255.0).clamp(0, 255).to(torch.uint8)   # truncation
     assert torch.equal(out, ref), f"mismatch {(out != ref).sum().item()} px"
+
+
+# ---- codec boundary: NV12 <-> RGB colour conversion next to NVDEC / NVENC -----------------------------------
+def _csc_ref(flags):
+    kr, kb = (0.299, 0.114) if flags & 1 else (0.2126, 0.0722)
+    yo, ys, cs = (0.0, 1.0, 1.0) if flags & 2 else (16.0, 219.0 / 255.0, 224.0 / 255.0)
+    return kr, 1.0 - kr - kb, kb, yo, ys, cs
+
+
+@pytest.mark.parametrize("flags", [0, 1, 2, 3])
+@pytest.mark.parametrize("h,w", [(64, 96), (512, 512), (30, 50)])
+def test_nv12_rgb_colour_conversion(cuda, flags, h, w):
+    """Both directions against the textbook BT.709 / BT.601 matrices (limited and full range), 2x2 chroma averaging."""
+    from ai_rtc_agent_b200.host import codec
+    g = torch.Generator().manual_seed(7)
+    rgb = torch.randint(0, 256, (1, 3, h, w), dtype=torch.uint8, generator=g)
+    kr, kg, kb, yo, ys, cs = _csc_ref(flags)
+    r, gg, b = (rgb[0, i].double() for i in range(3))
+    yl = kr * r + kg * gg + kb * b
+    y_ref = (yo + ys * yl).round().clamp(0, 255)
+    cb = (b - yl) / (2 * (1 - kb))
+    cr = (r - yl) / (2 * (1 - kr))
+    pool = lambda t: torch.nn.functional.avg_pool2d(t[None, None], 2, ceil_mode=True, count_include_pad=False)[0, 0]
+    cb_ref = (128 + cs * pool(cb)).round().clamp(0, 255)
+    cr_ref = (128 + cs * pool(cr)).round().clamp(0, 255)
+    y, uv = codec.rgb_to_nv12(rgb.to(cuda), flags)
+    assert (y.cpu().double() - y_ref).abs().max() <= 1
+    assert (uv.cpu()[:, 0::2].double()[:, :cb_ref.shape[1]] - cb_ref).abs().max() <= 1
+    assert (uv.cpu()[:, 1::2].double()[:, :cr_ref.shape[1]] - cr_ref).abs().max() <= 1
+    # decode direction: exact formula on the encoder's planes
+    back = codec.nv12_to_rgb(y, uv, flags).cpu()[0].double()      # (H,W,3)
+    yy = (y.cpu().double() - yo) / ys
+    up = lambda t: t.repeat_interleave(2, 0).repeat_interleave(2, 1)[:h, :w]
+    cbd = up((uv.cpu()[:, 0::2].double() - 128) / cs)
+    crd = up((uv.cpu()[:, 1::2].double() - 128) / cs)
+    rr = yy + 2 * (1 - kr) * crd
+    bb = yy + 2 * (1 - kb) * cbd
+    gr = (yy - kr * rr - kb * bb) / kg
+    ref = torch.stack([rr, gr, bb], dim=-1).round().clamp(0, 255)
+    assert (back - ref).abs().max() <= 1
+    # a smooth image survives the round trip closely (chroma sub-sampling aside)
+    xs = torch.linspace(0, 255, w)[None, :].expand(h, w)
+    smooth = torch.stack([xs, xs.flip(1), torch.full_like(xs, 128.0)]).round().to(torch.uint8)[None]
+    ys_, uvs = codec.rgb_to_nv12(smooth.to(cuda), flags)
+    rt = codec.nv12_to_rgb(ys_, uvs, flags).cpu()[0].permute(2, 0, 1).double()
+    assert (rt - smooth[0].double()).abs().max() <= 4
+
+
+def test_codec_sessions_report_unavailable(cuda):
+    from ai_rtc_agent_b200.host import codec
+    libs = codec.codec_libraries()
+    assert set(libs) == {"nvdec", "nvenc"}
+    with pytest.raises(codec.CodecUnavailable):
+        codec.open_decoder()
+    with pytest.raises(codec.CodecUnavailable):
+        codec.open_encoder()

@@ -82,3 +82,41 @@ def test_raw_weights_are_released_after_prepare(cuda):
     shape = (C.c_int64 * 4)(*t.shape)
     rc = sd._lib.b2sd_load_tensor(sd._handle, b"conv_in.weight", t.data_ptr(), 0, shape, 4)
     assert rc != 0 and b"released" in capi.lib().b2sd_last_error()
+
+
+def test_checkpoint_with_real_text_encoder_end_to_end(cuda, tmp_path, monkeypatch):
+    """No synthetic shortcut anywhere: UNet / TAESD / LoRAs from safetensors on disk, prompts through the checkpoint's own CLIP
+    text encoder (lib/wrapper.py:468-473) on prepare and on update_prompt (lib/pipeline.py:44-45, agent.py:166-168); frames
+    must track the oracle fed with the same embeddings."""
+    from ai_rtc_agent_b200.host import arch as A
+    from ai_rtc_agent_b200.host import weights as W
+    from ai_rtc_agent_b200.host.prompt import ClipPromptEncoder
+    from oracle import pipeline as opipe
+    from oracle import stream as ostream
+    from oracle import unet as ounet
+    from oracle import weights as ow
+    from tests.test_host import _write_tiny_checkpoint, _write_tiny_clip
+    monkeypatch.delenv("B200SD_SYNTHETIC_WEIGHTS", raising=False)
+    model_dir, taesd_dir, lcm_dir, style_path, *_ = _write_tiny_checkpoint(str(tmp_path))
+    _write_tiny_clip(model_dir, hidden=A.TINY_SD15.cross_attention_dim)
+    w = _wrapper(model_dir, taesd_dir, lcm_dir, style_path, str(tmp_path / "engines"))
+    assert isinstance(w.stream.prompt_encoder, ClipPromptEncoder)
+    # the oracle on the same (LoRA-fused) weights and the encoder's own embeddings
+    _, usd, vsd, _ = W.resolve_weights(model_dir, taesd_dir, lcm_dir, True, {style_path: 0.5}, sd_turbo=False)
+    cfg = ounet.tiny_config(False)
+    orc = ostream.StreamOracle(ow.to_float(usd), cfg, ow.to_float(vsd), [18, 26, 35, 45], 128, 128)
+    orc.prepare(w.stream.prompt_embeds[:1].float().cpu(), guidance_scale=0.0, init_noise=w.stream.init_noise.float())
+
+    def check(i):
+        f = ow.make_frame(128, 128, seed=i)
+        d = (w.stream.step_u8(f.cuda()).cpu().int() - opipe.frame_to_u8(orc, f).int()).abs()
+        assert (d <= 2).float().mean().item() >= 0.999 and d.max().item() <= 8, (i, d.max().item())
+
+    for i in range(3):
+        check(i)
+    before = w.stream.prompt_embeds.clone()
+    w.stream.update_prompt("a watercolor painting of a harbour")
+    assert not torch.equal(before, w.stream.prompt_embeds)
+    orc.update_prompt_embeds(w.stream.prompt_embeds[:1].float().cpu())
+    for i in range(3, 6):
+        check(i)
