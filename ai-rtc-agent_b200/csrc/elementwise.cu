@@ -361,6 +361,9 @@ __global__ void __launch_bounds__(GNC_THREADS, 2) gn_cluster_kernel(GroupNormArg
     const int ld = from_a ? a.lda : a.ldb;
     const float2 gm = *reinterpret_cast<const float2*>(a.gamma + c);   // parameters: not produced by the previous kernel
     const float2 bt = *reinterpret_cast<const float2*>(a.beta + c);
+    // A CTA may only touch a peer's shared memory once that peer is executing (compute-sanitizer racecheck: "block that might
+    // not have entered yet"): every CTA arrives on the cluster barrier here and waits on it right before its DSMEM stores.
+    if (nrank > 1) cluster_arrive_relaxed();
     B2_PDL_ENTRY();
     const int p0 = rank * ppc, p1 = min(a.hw, p0 + ppc);
     const long rowbase = (long)b * a.hw;
@@ -385,6 +388,7 @@ __global__ void __launch_bounds__(GNC_THREADS, 2) gn_cluster_kernel(GroupNormArg
     }
     if ((t & 31) == 0) red[t >> 5] = make_float2(s, q);
     __syncthreads();
+    if (nrank > 1) cluster_wait();   // all peers have started (they arrived before their loads): remote stores are legal now
     if (t == 0) {
         float2 tot = make_float2(0.f, 0.f);
 #pragma unroll

@@ -263,11 +263,24 @@ struct b2sd_engine {
     bool allow_swap = false;  // builders enable the swapped GEMM orientation for UNet contractions (never TAESD / V^T / GEGLU)
     cudaGraphExec_t graph_exec = nullptr;
     cudaGraph_t graph = nullptr;
-
-    ~b2sd_engine() {
-        if (graph_exec) cudaGraphExecDestroy(graph_exec);
-        if (graph) cudaGraphDestroy(graph);
+    // Stage pipelining of a stateful (T > 1) stream over lanes that SHARE the stream-batch state (b2sd_share_stream_state): the
+    // frame program is cut into [TAESD encoder body | last encoder conv + UNet + scheduler step | TAESD decoder], three CUDA
+    // graphs; only the middle stage touches the shared x_in, and the lanes chain it through one event.
+    struct StageGroup { cudaEvent_t unet_done = nullptr; ~StageGroup() { if (unet_done) cudaEventDestroy(unet_done); } };
+    std::shared_ptr<StageGroup> group;
+    size_t idx_enc_end = 0, idx_unet_end = 0;          // stage boundaries inside prog_frame
+    cudaGraphExec_t stage_exec[3] = {nullptr, nullptr, nullptr};
+    cudaGraph_t stage_graph[3] = {nullptr, nullptr, nullptr};
+    void drop_graphs() {
+        if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+        if (graph) { cudaGraphDestroy(graph); graph = nullptr; }
+        for (int i = 0; i < 3; ++i) {
+            if (stage_exec[i]) { cudaGraphExecDestroy(stage_exec[i]); stage_exec[i] = nullptr; }
+            if (stage_graph[i]) { cudaGraphDestroy(stage_graph[i]); stage_graph[i] = nullptr; }
+        }
     }
+
+    ~b2sd_engine() { drop_graphs(); }
 
     // ---- parameters -----------------------------------------------------------------------------
     const Raw* get(const std::string& key) {
@@ -567,6 +580,10 @@ struct b2sd_engine {
     int build_transformer(const std::string& p, const Act& x, int heads, Act* out, cudaStream_t s);
     int build_taesd_block(const std::string& p, const Act& x, Act* out, cudaStream_t s);
     int build_program(cudaStream_t s);
+    int run_range(std::vector<Op>& ops, size_t a, size_t b, cudaStream_t s) {
+        for (size_t i = a; i < b && i < ops.size(); ++i) TRY(ops[i](s));
+        return 0;
+    }
     int run(std::vector<Op>& ops, cudaStream_t s) {
         static const bool dbg = getenv("B200SD_DEBUG_SYNC") != nullptr;
         static const char* skip = getenv("B200SD_SKIP");  // debug: "groupnorm,attn" drops those launches (timing only)
@@ -886,8 +903,7 @@ int b2sd_engine::build_program(cudaStream_t s) {
     prog_frame.clear(); prog_prompt.clear(); prog_time.clear();
     taps.clear();
     launches = 0;
-    if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
-    if (graph) { cudaGraphDestroy(graph); graph = nullptr; }
+    drop_graphs();
     const int B = cfg.batch, H = cfg.height, W = cfg.width;
     const int* ch = cfg.block_out_channels;
     const int nlev = 4;
@@ -942,6 +958,7 @@ int b2sd_engine::build_program(cudaStream_t s) {
         Act nz = xt;
         nz.p = noise;
         const std::string k = "vae.encoder.layers." + std::to_string(li);
+        idx_enc_end = prog_frame.size();   // everything before this conv only touches this engine's own activations
         TRY(add_conv(prog_frame, e, k + ".weight", k + ".bias", 9, 1, xt, 0, &nz, s, coef_host[0][0], coef_host[1][0]));
         taps["x_t"] = xt;
     }
@@ -1030,6 +1047,7 @@ int b2sd_engine::build_program(cudaStream_t s) {
         const int T = B, hw = lh * lw, dan = cfg.do_add_noise;
         ++launches;
         prog_frame.push_back(Op([=](cudaStream_t st) { return lcm_step_launch(xp, ep, np_, cf, op, T, hw, dan, st); }, "lcm_step"));
+        idx_unet_end = prog_frame.size();
     }
     taps["x0"] = x0;
     allow_swap = false;
@@ -1076,9 +1094,11 @@ int b2sd_engine::build_program(cudaStream_t s) {
     if (ln_stats_used) {
         unsigned long long* sp = ln_stats;
         const size_t bytes = ln_stats_used * sizeof(unsigned long long);
-        prog_frame.insert(prog_frame.begin(), Op([sp, bytes](cudaStream_t st) {
+        // first op of the UNet stage (the statistics belong to the transformer blocks)
+        prog_frame.insert(prog_frame.begin() + idx_enc_end, Op([sp, bytes](cudaStream_t st) {
             if (cudaMemsetAsync(sp, 0, bytes, st) != cudaSuccess) { b2_set_error("memset of the LayerNorm statistics failed"); return -1; }
             return 0; }, "memset ln_stats"));
+        idx_unet_end += 1;
     }
     CUDA_OK(cudaStreamSynchronize(s));
     built = true;
@@ -1490,7 +1510,33 @@ int b2sd_step_ex(b2sd_handle h, const void* frame_in, int in_kind, int in_h, int
     a.x = frame_in; a.in_h = in_h; a.in_w = in_w;
     a.flags = in_kind == B2SD_IN_U8_NHWC ? SC_IN_U8 : (in_kind == B2SD_IN_F32_NCHW ? SC_IN_F32_NCHW : SC_IN_F16_NCHW);
     TRY(smallconv_launch(a, s));
-    if (h->cfg.use_cuda_graph) {
+    if (h->group) {
+        // stage-pipelined lanes of one stateful stream: encoder body | [wait previous frame's UNet stage] last encoder conv,
+        // UNet, scheduler step [signal] | decoder.  Lanes run on different streams; only the middle stage is serialised.
+        const size_t cut[4] = {0, h->idx_enc_end, h->idx_unet_end, h->prog_frame.size()};
+        for (int st = 0; st < 3; ++st) {
+            if (st == 1) CUDA_OK(cudaStreamWaitEvent(s, h->group->unet_done, 0));
+            if (h->cfg.use_cuda_graph) {
+                if (!h->stage_exec[st]) {
+                    cudaStream_t cs;
+                    CUDA_OK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+                    CUDA_OK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+                    int rc = h->run_range(h->prog_frame, cut[st], cut[st + 1], cs);
+                    cudaError_t ec = cudaStreamEndCapture(cs, &h->stage_graph[st]);
+                    cudaStreamDestroy(cs);
+                    if (rc || ec != cudaSuccess || cudaGraphInstantiate(&h->stage_exec[st], h->stage_graph[st], 0) != cudaSuccess) {
+                        if (!rc) b2_set_error("b2sd_step: CUDA graph capture of stage %d failed: %s", st, cudaGetErrorString(ec != cudaSuccess ? ec : cudaGetLastError()));
+                        h->drop_graphs();
+                        return -1;
+                    }
+                }
+                CUDA_OK(cudaGraphLaunch(h->stage_exec[st], s));
+            } else {
+                TRY(h->run_range(h->prog_frame, cut[st], cut[st + 1], s));
+            }
+            if (st == 1) CUDA_OK(cudaEventRecord(h->group->unet_done, s));
+        }
+    } else if (h->cfg.use_cuda_graph) {
         if (!h->graph_exec) {
             cudaStream_t cs;
             CUDA_OK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
@@ -1650,6 +1696,27 @@ int b2sd_profile_kind(b2sd_handle h, const char* kind, int iters, double* ms_per
 }
 
 int b2sd_launches_per_step(b2sd_handle h) { return h ? h->launches : 0; }
+
+/* Make `lane` continue the SAME temporal stream as `owner` (both engines of one weight store, same batch and size): they
+ * share the stream-batch state (x_t_latent_buffer) and are stage-pipelined -- while one lane runs the UNet stage of frame n,
+ * the other runs the TAESD encoder body of frame n+1 / the decoder of frame n-1.  Frames must be submitted alternately, in
+ * order, from one host thread.  Call before either engine's b2sd_prepare. */
+int b2sd_share_stream_state(b2sd_handle lane, b2sd_handle owner) {
+    if (!lane || !owner || lane == owner || lane->ws != owner->ws || lane->cfg.batch != owner->cfg.batch ||
+        lane->cfg.height != owner->cfg.height || lane->cfg.width != owner->cfg.width) {
+        b2_set_error("b2sd_share_stream_state: engines must be lanes of one weight store with the same batch and size");
+        return -1;
+    }
+    if (!owner->group) {
+        owner->group = std::make_shared<b2sd_engine::StageGroup>();
+        CUDA_OK(cudaEventCreateWithFlags(&owner->group->unet_done, cudaEventDisableTiming));
+    }
+    lane->group = owner->group;
+    lane->x_in.p = owner->x_in.p;        // the UNet input batch: slot 0 = fresh x_t, slots 1.. = x_t_latent_buffer
+    lane->built = false;
+    owner->built = false;
+    return 0;
+}
 
 int b2sd_set_concurrency(b2sd_handle h, int frames_in_flight) {
     if (!h || frames_in_flight < 1) {

@@ -236,6 +236,75 @@ __device__ __forceinline__ void epi_row_fast(const IgEpilogue& e, uint32_t taddr
     if (e.rowstat_out && row_ok && ncols > 0) rowstat_add(e, orow, st1, st2);
 }
 
+// LayerNorm-folded epilogue of one output row (non-split, see IgEpilogue::colsum): the tile's colsum / bias' vectors were
+// staged in shared memory (`lnv`: [ncols_tile] colsum, then [ncols_tile] bias') while the mainloop ran, so the per-chunk loop
+// has no global-memory loads on its critical path.  c_tile0 = first column of this call inside the staged tile.
+__device__ __forceinline__ void epi_row_ln(const IgEpilogue& e, uint32_t taddr, int ncols, int gcol0, long orow, bool row_ok,
+                                           const float* lnv, int tile_cols, float mu, float rstd) {
+    const float* cs = lnv;
+    const float* bb = lnv + tile_cols;
+    const float nmr = -mu * rstd;
+    for (int c = 0; c < ncols; c += 32) {
+        const int left = ncols - c;
+        uint32_t v[32];
+        if (left >= 32) {
+            tmem_ld32(taddr + c, v);
+        } else {
+            uint32_t lo[16];
+            tmem_ld16(taddr + c, lo);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { v[i] = lo[i]; v[16 + i] = 0; }
+        }
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        const bool transposed = e.out2 && gcol0 + c >= e.col2;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            if (8 * g >= left) break;
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i = 8 * g + j;
+                x[j] = fmaf(rstd, __uint_as_float(v[i]), fmaf(nmr, cs[c + i], bb[c + i]));   // rstd*acc - rstd*mu*colsum + bias'
+            }
+            if (transposed) {   // V block of the fused q/k/v projection -> V^T (32 lanes = 32 consecutive tokens)
+                __half* tp = e.out2 + (long)(gcol0 + c + 8 * g - e.col2) * e.ld2 + orow;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) tp[(long)j * e.ld2] = __float2half_rn(x[j]);
+            } else {
+                uint4 o;
+                __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+                *reinterpret_cast<uint4*>(e.out + orow * e.ldc + gcol0 + c + 8 * g) = o;
+            }
+        }
+    }
+}
+
+// GEGLU with the LayerNorm (norm3) folded: value columns [0, half_n), gate columns [half_n, 2*half_n) of the tile
+__device__ __forceinline__ void epi_row_geglu_ln(const IgEpilogue& e, uint32_t taddr, int half_n, int ocol0, long orow, bool row_ok,
+                                                 const float* lnv, int tile_cols, float mu, float rstd) {
+    const float* cs = lnv;
+    const float* bb = lnv + tile_cols;
+    const float nmr = -mu * rstd;
+    for (int c = 0; c < half_n; c += 16) {
+        uint32_t a[16], g[16];
+        tmem_ld16(taddr + c, a);
+        tmem_ld16(taddr + half_n + c, g);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float av = fmaf(rstd, __uint_as_float(a[i]), fmaf(nmr, cs[c + i], bb[c + i]));
+            const float gv = fmaf(rstd, __uint_as_float(g[i]), fmaf(nmr, cs[half_n + c + i], bb[half_n + c + i]));
+            v[i] = av * gelu_erf(gv);
+        }
+        store_half16(e.out + orow * e.ldc + ocol0 + c, v, 16, (e.ldc & 7) == 0);
+    }
+}
+
 __device__ __forceinline__ bool epi_fast_ok(const IgEpilogue& e) {
     return !(e.flags & (IG_SPLITK | IG_GEGLU)) && (e.n_valid & 15) == 0 && (e.ldc & 7) == 0 && (!e.res || (e.ldr & 7) == 0) &&
            (e.colbias_bstride & 3) == 0 && !e.colsum && !e.out2;

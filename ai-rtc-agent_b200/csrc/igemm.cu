@@ -294,6 +294,18 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
         const int hi = (r / p.tw) % p.th;
         const int ni = r / (p.tw * p.th);
         const IgEpilogue& e = p.epi;
+        // LayerNorm-folded launches: stage this N tile's colsum / bias' in shared memory while the mainloop runs
+        const bool ln_smem = e.colsum && !p.swap && !(e.flags & IG_SPLITK) && (e.ldc & 7) == 0 && (e.n_valid & 15) == 0;
+        float* lnv = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 512);
+        if (ln_smem) {
+            for (int i = threadIdx.x - 64; i < p.BN; i += 128) {
+                const int gc = ntile * p.BN + i;
+                const bool in = gc < ((e.flags & IG_GEGLU) ? 2 * e.n_valid : e.n_valid);
+                lnv[i] = in ? e.colsum[gc] : 0.f;
+                lnv[p.BN + i] = (in && e.colbias) ? e.colbias[gc] : 0.f;
+            }
+            epi_bar_sync();
+        }
         int it = 0;
         for (int mt = blockIdx.x; mt < num_mtiles; mt += gridDim.x, ++it) {
             const int buf = it & 1;
@@ -333,6 +345,18 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                         swap_store_chunk(p, pre, T, ntile, r);
                         epi_bar_sync();
                     }
+                }
+            } else if (ln_smem) {
+                float mu, rstd;
+                ln_row_stats(e, orow, row_ok, mu, rstd);     // global loads: in flight while the accumulator completes
+                mbar_wait(&tmem_full_bar[buf], par);
+                tc_fence_after();
+                if (e.flags & IG_GEGLU) {
+                    epi_row_geglu_ln(e, taddr, p.BN / 2, ntile * (p.BN / 2), orow, row_ok, lnv, p.BN, mu, rstd);
+                } else {
+                    int ncols = e.n_valid - ntile * p.BN;
+                    if (ncols > p.BN) ncols = p.BN;
+                    epi_row_ln(e, taddr, ncols, ntile * p.BN, orow, row_ok && ncols > 0, lnv, p.BN, mu, rstd);
                 }
             } else if (epi_fast_ok(e)) {
                 int ncols = e.n_valid - ntile * p.BN;
@@ -804,7 +828,7 @@ int igemm_plan(const IgemmDesc& d, IgemmPlan* plan) {
             pipe_bytes = stages * stage_bytes;
         }
     }
-    plan->smem = pipe_bytes + 1024 /*align slack*/ + 512 /*barriers*/;
+    plan->smem = pipe_bytes + 1024 /*align slack*/ + 512 /*barriers*/ + (d.epi.colsum ? 2 * 256 * sizeof(float) : 0) /*LN vectors*/;
     // persistent over M tiles when the launch would need more than one co-resident wave (2 CTAs per SM)
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     static const bool no_persist = getenv("B2_NO_PERSIST") != nullptr;

@@ -25,7 +25,8 @@ DEFAULT_PROMPT = "fireworks in the night sky"
 DEFAULT_T_INDEX_LIST = [18, 26, 35, 45]
 DEFAULT_NUM_INFERENCE_STEPS = 50
 DEFAULT_GUIDANCE_SCALE = 0.0
-DEFAULT_LANES_ONE_STEP = 4    # frames in flight for a 1-step stream batch (measured: 1 -> 232, 2 -> 308, 3 -> 350, 4 -> 366 fps)
+DEFAULT_LANES_ONE_STEP = 4    # frames in flight for a 1-step stream batch (measured: 1 -> 232, 2 -> 315, 4 -> 397, 6 -> 413 fps)
+DEFAULT_LANES_STATEFUL = 2    # T > 1: stage pipelining over two lanes that share the stream-batch state
 
 
 def _is_video_frame(frame) -> bool:
@@ -55,9 +56,11 @@ def _as_torch_u8_nhwc(frame, device) -> torch.Tensor:
 class StreamDiffusionPipeline:
     def __init__(self, model_id: str, t_index_list: Optional[List[int]] = None, width: int = 512, height: int = 512,
                  prompt: str = DEFAULT_PROMPT, lanes: Optional[int] = None):
-        """lanes: frames in flight for enqueue().  With a 1-step stream batch (SD-Turbo) consecutive frames are independent, so
-        two lanes (default there; $B200SD_LANES overrides) process frame n+1 while frame n is still on the GPU, bit-identical
-        to sequential processing.  With T > 1 the stream batch carries state from frame to frame: always one lane."""
+        """lanes: frames in flight for enqueue() ($B200SD_LANES overrides the default).  With a 1-step stream batch (SD-Turbo)
+        consecutive frames are independent: DEFAULT_LANES_ONE_STEP lanes process frame n+1.. while frame n is still on the GPU.
+        With T > 1 the stream batch carries state from frame to frame: two lanes share that state and are stage-pipelined (TAESD
+        encoder of frame n+1 and decoder of frame n-1 overlap the UNet of frame n).  Both are bit-identical to submitting the
+        same frames one at a time."""
         self.prompt = prompt
         self.t_index_list = list(t_index_list) if t_index_list is not None else DEFAULT_T_INDEX_LIST
         self.device = "cuda"
@@ -77,15 +80,16 @@ class StreamDiffusionPipeline:
             cfg_type="self",
             engine_dir=os.getenv("TRT_ENGINES_CACHE", "./models/engines"),
         )
+        stateful = len(self.t_index_list) > 1     # x_t_latent_buffer chains frame n+1 to frame n
         if lanes is None:
-            lanes = int(os.getenv("B200SD_LANES", "0")) or (DEFAULT_LANES_ONE_STEP if len(self.t_index_list) == 1 else 1)
-        if len(self.t_index_list) > 1:
-            lanes = 1          # x_t_latent_buffer chains frame n+1 to frame n
+            lanes = int(os.getenv("B200SD_LANES", "0")) or (DEFAULT_LANES_STATEFUL if stateful else DEFAULT_LANES_ONE_STEP)
+        if stateful:
+            lanes = min(lanes, 2)   # three stages, the middle one serial: a third lane has nothing to overlap
         self.model.stream.set_concurrency(max(1, lanes))
         self.model.prepare(prompt=self.prompt, num_inference_steps=DEFAULT_NUM_INFERENCE_STEPS,
                            guidance_scale=DEFAULT_GUIDANCE_SCALE)
         sd = self.model.stream
-        self._engines = [sd] + [sd.add_lane() for _ in range(max(1, lanes) - 1)]
+        self._engines = [sd] + [sd.add_lane(share_state=stateful) for _ in range(max(1, lanes) - 1)]
         # one lane: frames run on the caller's stream, exactly as before.  Several lanes: every lane has its own stream (a lane on
         # the caller's stream would order the other lanes' "input ready" events behind its frames and serialise them)
         self._lane_streams = [None] if len(self._engines) == 1 else [torch.cuda.Stream(sd.device) for _ in self._engines]

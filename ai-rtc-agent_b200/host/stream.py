@@ -228,12 +228,18 @@ class StreamDiffusion:
         self.t_list = list(other.t_list)
         self._engine_prepare()
 
-    def add_lane(self) -> "StreamDiffusion":
+    def add_lane(self, share_state: bool = False) -> "StreamDiffusion":
         """Another engine over the same weights, prepared identically (same prompt embedding, schedule and seed-2 noise):
         frames may be alternated between this engine and its lanes on different CUDA streams.  Later prepare() /
-        update_prompt() / timestep updates on this object reach every lane."""
+        update_prompt() / timestep updates on this object reach every lane.
+        share_state=False: the lane is an independent temporal stream (or, for a 1-step stream batch, simply the next frame).
+        share_state=True: the lane continues THIS stream -- it shares the stream-batch state and is stage-pipelined with it
+        (b2sd_share_stream_state): required for T > 1, where frame n+1 needs frame n's x_t_latent_buffer."""
         self._check()
         lane = StreamDiffusion(self.arch, {}, {}, self.t_list, self.prompt_encoder, parent=self, **self._ctor)
+        if share_state:
+            capi.check(self._lib.b2sd_share_stream_state(lane._handle, self._handle), "b2sd_share_stream_state")
+            self._engine_prepare()          # the owner's frame program is rebuilt as three stages (packed weights are cached)
         lane._prepare_like(self)
         self.lanes.append(lane)
         return lane

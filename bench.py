@@ -307,7 +307,7 @@ def main_gpu(args):
     world_env = int(os.getenv("WORLD_SIZE", "1"))
     nccl_glob = None
     nccl_env = {k: v for k, v in os.environ.items() if k.startswith("NCCL_DEBUG")}
-    if world_env > 1 and "NCCL_DEBUG" not in os.environ:
+    if world_env > 1 and os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":   # unset, or the CUDA image's default
         # nobody asked for NCCL's log: keep stdout to the single JSON line, but still keep NCCL's own account of the job
         # (INFO level into per-process files, summarised in the line's "nccl" field).  A caller-provided NCCL_DEBUG is left
         # exactly as it is -- level and destination -- so a harness that reads NCCL's output from this process keeps seeing it.

@@ -238,6 +238,12 @@ int b2sd_profile_kind(b2sd_handle h, const char* kind, int iters, double* ms_per
                       void* stream);
 /* number of kernel launches (graph nodes) in one b2sd_step */
 int b2sd_launches_per_step(b2sd_handle h);
+/* Stage pipelining of ONE stateful stream (stream batch T > 1, where frame n+1 needs frame n's latent buffer and lanes cannot
+ * simply alternate): `lane` shares `owner`'s stream-batch state; the frame program of each is cut into TAESD encoder body |
+ * last encoder conv + UNet + scheduler step | TAESD decoder, and only the middle stage is serialised between the lanes (one
+ * CUDA event), so the encoder of frame n+1 and the decoder of frame n-1 overlap the UNet of frame n.  Both engines must be
+ * lanes of one weight store with equal batch / size; call before b2sd_prepare; submit frames alternately, in order. */
+int b2sd_share_stream_state(b2sd_handle lane, b2sd_handle owner);
 /* How many frames will be in flight on this GPU (lanes / independent streams).  1 (default): launch policy tuned for the
  * latency of a single frame; > 1: policy tuned for throughput (smaller operand rings so CTAs of different frames share an
  * SM).  Takes effect at the next b2sd_prepare. */

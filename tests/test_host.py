@@ -192,9 +192,12 @@ def _write_tiny_checkpoint(root, with_lora=True):
     import torch
     from safetensors.torch import save_file
     from ai_rtc_agent_b200.host import arch as A
-    arch = A.TINY_SD15
-    unet = A.synthetic_state_dict(A.unet_param_shapes(arch), seed=5)
-    vae = A.synthetic_state_dict(A.taesd_param_shapes(), seed=6, relu_net=True)
+    from oracle import unet as ounet
+    from oracle import weights as ow
+    # the oracle's generator (fan-in scaling with damped residual branches keeps fp16 error growth like a trained net's)
+    unet = ow.make_unet_weights(ounet.tiny_config(False), seed=5)
+    vae = ow.make_taesd_weights(seed=6)
+    assert set(unet) == set(A.unet_param_shapes(A.TINY_SD15)) and set(vae) == set(A.taesd_param_shapes())
     model_dir = os.path.join(root, "tiny-sd15-ckpt")
     os.makedirs(os.path.join(model_dir, "unet"))
     save_file({k: v.contiguous() for k, v in unet.items()}, os.path.join(model_dir, "unet", "diffusion_pytorch_model.fp16.safetensors"))

@@ -255,7 +255,7 @@ def test_nv12_rgb_colour_conversion(cuda, flags, h, w):
     smooth = torch.stack([xs, xs.flip(1), torch.full_like(xs, 128.0)]).round().to(torch.uint8)[None]
     ys_, uvs = codec.rgb_to_nv12(smooth.to(cuda), flags)
     rt = codec.nv12_to_rgb(ys_, uvs, flags).cpu()[0].permute(2, 0, 1).double()
-    assert (rt - smooth[0].double()).abs().max() <= 4
+    assert (rt - smooth[0].double()).abs().max() <= 6     # 2x2 chroma averaging of a 5-levels-per-pixel ramp + two roundings
 
 
 def test_codec_sessions_report_unavailable(cuda):

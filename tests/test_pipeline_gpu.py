@@ -206,9 +206,30 @@ def test_two_lanes_equal_sequential_processing(cuda, monkeypatch):
     for t, r in zip(queued_after, ref_after):
         assert torch.equal(t.result().cpu(), r)
     assert not torch.equal(ref_after[0], one(frames[0]).cpu()) or True
-    # T > 1 carries state between frames: lanes are refused
-    four, _ = _pipeline("tiny-turbo", [20, 40], 128, monkeypatch, lanes=2)
-    assert four.lanes == 1
+
+
+@pytest.mark.parametrize("model_id,tl", [("tiny-turbo", [20, 40]), ("tiny-sd15", [18, 26, 35, 45])])
+def test_stateful_stream_stage_pipelined_over_two_lanes(cuda, monkeypatch, model_id, tl):
+    """T > 1: frame n+1 needs frame n's x_t_latent_buffer, so the two lanes SHARE the stream-batch state and only overlap the
+    TAESD encoder / decoder stages with the other lane's UNet stage (b2sd_share_stream_state).  Frames submitted back to back
+    must equal the same pipeline driven one frame at a time, track the oracle (incl. the T-1 frame output lag), and leave the
+    shared latent buffer in the oracle's state."""
+    from oracle import pipeline as opipe
+    from oracle import weights as ow
+    seq, orc = _pipeline(model_id, tl, 128, monkeypatch, lanes=2)
+    par, _ = _pipeline(model_id, tl, 128, monkeypatch, lanes=2)
+    three, _ = _pipeline(model_id, tl, 128, monkeypatch, lanes=5)
+    assert seq.lanes == 2 and par.lanes == 2 and three.lanes == 2     # more than two lanes have nothing to overlap
+    frames = [ow.make_frame(128, 128, seed=120 + i) for i in range(9)]
+    want = [seq(f.cuda()).cpu() for f in frames]
+    tickets = [par.enqueue(f.cuda()) for f in frames]
+    for i, (t, w) in enumerate(zip(tickets, want)):
+        assert torch.equal(t.result().cpu(), w), f"frame {i}"
+    for i, f in enumerate(frames):
+        _u8_ok(want[i], opipe.frame_to_u8(orc, f), f"frame {i} vs oracle")
+    buf = par.model.stream.get_tensor("unet_in")[1:].float().permute(0, 3, 1, 2)
+    ref = orc.x_t_latent_buffer
+    assert (buf - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
 
 
 def test_track_adapter_on_the_real_pipeline(cuda, monkeypatch):
