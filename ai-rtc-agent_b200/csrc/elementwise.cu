@@ -481,7 +481,6 @@ int groupnorm_launch(const GroupNormArgs& a, cudaStream_t s) {
     size_t smem = (size_t)rpi * C * 2 * sizeof(float);
     if (smem < 16 * 64 * 2 * sizeof(float)) smem = 16 * 64 * 2 * sizeof(float);  // also the stats-finalise scratch
     static bool attr = false;
-    static int max_coop_blocks_per_sm = 0;
     if (!attr) {
         cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -490,7 +489,6 @@ int groupnorm_launch(const GroupNormArgs& a, cudaStream_t s) {
     // single cooperative launch when the whole grid is co-resident and a chunk fits the register cache
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel, threads, smem);
-    (void)max_coop_blocks_per_sm;
     const bool fits = (ppc + rpi - 1) / rpi <= GN_CACHE && (long)nchunks * a.nb <= (long)per_sm * 148 && a.nb <= 16;
     if (fits && a.counters) {
         cudaLaunchConfig_t cfg{};

@@ -704,12 +704,12 @@ int b2sd_engine::build_transformer(const std::string& p, const Act& x, int heads
     // whose epilogue also accumulates the row statistics (rowstat_out); the consumer GEMM runs on the RAW rows with gamma folded
     // into its weights and applies mean / rstd in its epilogue (IgEpilogue::colsum).  B2_NO_LNFOLD=1 restores the three
     // layernorm launches + separate V^T GEMM (also used when the batch's V^T columns need per-image padding).
-    // Measured (profiles/ab_sd15_r02i.txt): at 4096 tokens (batch 1, 512x512) the fold saves 0.12 ms per frame -- every launch there
-    // is latency; at 16384+ tokens (4-step stream batch) the folded epilogues (per-column colsum / bias', 2-byte transposed V
-    // stores, statistics atomics) cost more than the three layernorm launches they replace (+0.4 ms), so large batches keep them.
+    // Measured (profiles/ab_sd15_r02l.txt, ab_r02l.txt), with the consumer's colsum / bias' vectors staged in shared memory:
+    // SD-Turbo 512x512 4 lanes 380 -> 421 fps, SD-1.5 4-step 512x512 124 -> 133 fps, 768x768 50.1 -> 52.9 fps.  (A first
+    // version that read those vectors from global memory inside the per-chunk loop LOST 5 % at 16384 tokens.)
     static const bool no_fold = getenv("B2_NO_LNFOLD") != nullptr;
-    static const char* fold_rows_env = getenv("B2_LNFOLD_MAX_ROWS");
-    const long fold_max_rows = fold_rows_env ? atol(fold_rows_env) : 4096;
+    static const char* fold_rows_env = getenv("B2_LNFOLD_MAX_ROWS");   // tuning: disable the fold above this many tokens
+    const long fold_max_rows = fold_rows_env ? atol(fold_rows_env) : (1l << 40);
     const bool fold = !no_fold && one_gemm && (long)B * (cfg.height / 8) * (cfg.width / 8) <= fold_max_rows;
     const int inner = 4 * C;
     std::vector<int> gperm;   // GEGLU: weight rows interleaved per 128-wide tile as [64 value | 64 gate]
