@@ -75,7 +75,8 @@ if "tilesweep" in sys.argv:
                 except Exception as e: print("fail", h, cin, cout, bn, sp, str(e)[:80])
     sys.exit(0)
 if "boundstudy" in sys.argv:
-    print("B2_DBG_MODE =", os.environ.get("B2_DBG_MODE", "0"), "(0 normal, 1 no TMA after first ring pass, 2 no MMAs)")
+    print("B2_DBG_MODE =", os.environ.get("B2_DBG_MODE", "0"), "(0 normal, 1 no TMA after first ring pass, 2 no MMAs; needs the "
+          "bound-study build: make -C ai-rtc-agent_b200/csrc boundstudy; B200SD_LIB=ai-rtc-agent_b200/libb200sd_bs.so)")
     for (h, cin, cout, taps, bn, sp, sw) in [(64, 320, 320, 9, 64, 1, False), (64, 320, 320, 9, 160, 1, False), (64, 320, 320, 9, 128, 1, True), (64, 320, 320, 9, 256, 2, True),
                                              (32, 640, 640, 9, 64, 2, False), (32, 640, 640, 9, 256, 4, True),
                                              (16, 1280, 1280, 9, 64, 4, False), (16, 1280, 1280, 9, 256, 8, True), (16, 1280, 1280, 9, 128, 4, True),
