@@ -330,3 +330,21 @@ def test_clip_prompt_encoder_from_a_checkpoint_directory(tmp_path):
     assert torch.allclose(b.float(), ref(ids)[0].float(), atol=2e-2)
     with pytest.raises(ValueError, match="hidden size"):
         make_prompt_encoder(d, 768, "cpu")    # encoder / UNet mismatch must not pass silently
+
+
+def test_bench_helpers(tmp_path, monkeypatch):
+    """bench.py's host-side helpers: NCCL log summary (what the multi-GPU line reports as evidence of the communicator), core
+    count for the CPU arm (torchrun's OMP_NUM_THREADS=1 must not decide it), one config dict for every arm."""
+    sys.path.insert(0, ROOT)
+    import bench
+    log = tmp_path / "nccl_n2_host_123.log"
+    log.write_text("host:123:123 [0] NCCL INFO NCCL version 2.28.9+cuda12.9\n"
+                   "host:123:456 [0] NCCL INFO Channel 00/0 : 0[0] -> 1[1] via P2P/CUMEM\n"
+                   "host:123:456 [0] NCCL INFO comm 0x1 rank 0 nranks 2 cudaDev 0 nvmlDev 0 busId 1b000 commId 0x2 - Init COMPLETE\n")
+    s = bench.nccl_log_summary(str(tmp_path / "nccl_n2_*_*.log"))
+    assert s["init_complete_nranks"] == [2] and s["version"] == "2.28.9" and s["p2p_seen"] and not s["nvls_seen"]
+    monkeypatch.setenv("OMP_NUM_THREADS", "1")
+    assert 1 <= bench.physical_cores() <= (os.cpu_count() or 1)
+    assert bench.bench_config(1)["workload"] == bench.bench_config(8)["workload"]
+    assert set(bench.bench_config(1)) == set(bench.bench_config(8))
+    assert bench.pin_to_gpu_numa_node(0) is None or "numa_node" in bench.pin_to_gpu_numa_node(0)
