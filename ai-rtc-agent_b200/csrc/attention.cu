@@ -41,9 +41,14 @@ struct AttnParams {
     float scale_log2;
 };
 
-template <int DA, int BKV>
+// PTS = true: P (the softmax numerators, fp16) goes to tensor memory and the P.V product reads its A operand from there
+// (tcgen05.mma "TS" form) -- no 32 KB shared-memory round trip of P per KV block.  TMEM columns: S [0,BKV) fp32,
+// O [BKV, BKV+DP) fp32, P [BKV+DP, BKV+DP+BKV/2) packed fp16: 256 for <1,128>, so two CTAs still share an SM.
+template <int DA, int BKV, bool PTS = false>
 __global__ void __launch_bounds__(AT_THREADS, (DA == 1 ? 2 : 1)) attn_kernel(const __grid_constant__ AttnParams p) {
     constexpr int DP = DA * 64;
+    static_assert(!PTS || BKV + DP + BKV / 2 <= (int)AT_TMEM_COLS, "P does not fit the CTA's tensor memory");
+    constexpr int NST = PTS ? AT_STAGES + 1 : AT_STAGES;   // the 32 KB the P tile no longer needs in shared memory buy a third K/V stage
     constexpr int KVA = BKV / 64;                       // kv atoms per block (P / V^T tiles)
     constexpr uint32_t Q_BYTES = DA * AT_BQ * 128;      // DA atoms of [128 rows][128 B]
     constexpr uint32_t K_BYTES = DA * BKV * 128;        // DA atoms of [BKV rows][128 B]
@@ -54,14 +59,14 @@ __global__ void __launch_bounds__(AT_THREADS, (DA == 1 ? 2 : 1)) attn_kernel(con
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sQ = smem;
     uint8_t* sKV = sQ + Q_BYTES;
-    uint8_t* sP = sKV + AT_STAGES * STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+    uint8_t* sP = sKV + NST * STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (PTS ? 0 : P_BYTES));
     uint64_t* q_full = bars;
-    uint64_t* k_full = bars + 1;                // [AT_STAGES]  K and V^T tiles travel through separate rings: a K slot is
-    uint64_t* k_empty = k_full + AT_STAGES;     // [AT_STAGES]  free as soon as QK^T(j) retires, one softmax earlier than the
-    uint64_t* v_full = k_empty + AT_STAGES;     // [AT_STAGES]  V slot, so K(j+2) is requested ~1.3 KV blocks before its use
-    uint64_t* v_empty = v_full + AT_STAGES;     // [AT_STAGES]  (with one shared ring the K latency was exposed every block)
-    uint64_t* s_full = v_empty + AT_STAGES;
+    uint64_t* k_full = bars + 1;                // [NST]  K and V^T tiles travel through separate rings: a K slot is
+    uint64_t* k_empty = k_full + NST;     // [NST]  free as soon as QK^T(j) retires, one softmax earlier than the
+    uint64_t* v_full = k_empty + NST;     // [NST]  V slot, so K(j+2) is requested ~1.3 KV blocks before its use
+    uint64_t* v_empty = v_full + NST;     // [NST]  (with one shared ring the K latency was exposed every block)
+    uint64_t* s_full = v_empty + NST;
     uint64_t* s_empty = s_full + 1;
     uint64_t* p_full = s_empty + 1;
     uint64_t* o_done = p_full + 1;
@@ -82,7 +87,7 @@ __global__ void __launch_bounds__(AT_THREADS, (DA == 1 ? 2 : 1)) attn_kernel(con
         tma_prefetch_desc(&p.tmk);
         tma_prefetch_desc(&p.tmv);
         mbar_init(q_full, 1);
-        for (int s = 0; s < AT_STAGES; ++s) {
+        for (int s = 0; s < NST; ++s) {
             mbar_init(&k_full[s], 1);
             mbar_init(&k_empty[s], 1);
             mbar_init(&v_full[s], 1);
@@ -113,8 +118,8 @@ __global__ void __launch_bounds__(AT_THREADS, (DA == 1 ? 2 : 1)) attn_kernel(con
             for (int a = 0; a < DA; ++a)
                 tma_load_2d(sQ + a * (AT_BQ * 128), &p.tmq, q_full, h * DP + a * 64, b * p.sq + q0);
             auto load_k = [&](int j) {
-                const int st = j % AT_STAGES;
-                mbar_wait(&k_empty[st], ((j / AT_STAGES) & 1) ^ 1);
+                const int st = j % NST;
+                mbar_wait(&k_empty[st], ((j / NST) & 1) ^ 1);
                 uint8_t* sk = sKV + st * STAGE_BYTES;
                 mbar_expect_tx(&k_full[st], K_BYTES);
 #pragma unroll
@@ -122,8 +127,8 @@ __global__ void __launch_bounds__(AT_THREADS, (DA == 1 ? 2 : 1)) attn_kernel(con
                     tma_load_2d(sk + a * (BKV * 128), &p.tmk, &k_full[st], h * DP + a * 64, (int)(b * p.k_bstride) + j * BKV);
             };
             auto load_v = [&](int j) {
-                const int st = j % AT_STAGES;
-                mbar_wait(&v_empty[st], ((j / AT_STAGES) & 1) ^ 1);
+                const int st = j % NST;
+                mbar_wait(&v_empty[st], ((j / NST) & 1) ^ 1);
                 uint8_t* sv = sKV + st * STAGE_BYTES + K_BYTES;
                 mbar_expect_tx(&v_full[st], V_BYTES);
 #pragma unroll
@@ -144,8 +149,8 @@ __global__ void __launch_bounds__(AT_THREADS, (DA == 1 ? 2 : 1)) attn_kernel(con
         const uint32_t idesc_o = make_idesc_f16(AT_BQ, DP);
         const uint32_t sq_addr = smem_u32(sQ), skv_addr = smem_u32(sKV), sp_addr = smem_u32(sP);
         auto issue_qk = [&](int j) {
-            const int st = j % AT_STAGES;
-            mbar_wait(&k_full[st], (j / AT_STAGES) & 1);
+            const int st = j % NST;
+            mbar_wait(&k_full[st], (j / NST) & 1);
             mbar_wait(s_empty, (j & 1) ^ 1);
             tc_fence_after();
             const uint32_t sk = skv_addr + st * STAGE_BYTES;
@@ -166,8 +171,8 @@ __global__ void __launch_bounds__(AT_THREADS, (DA == 1 ? 2 : 1)) attn_kernel(con
         issue_qk(0);
         for (int j = 0; j < nblk; ++j) {
             if (j + 1 < nblk) issue_qk(j + 1);  // issues as soon as softmax(j) has drained S; overlaps its P stores
-            const int st = j % AT_STAGES;
-            mbar_wait(&v_full[st], (j / AT_STAGES) & 1);
+            const int st = j % NST;
+            mbar_wait(&v_full[st], (j / NST) & 1);
             mbar_wait(p_full, j & 1);
             tc_fence_after();
             const uint32_t sv = skv_addr + st * STAGE_BYTES + K_BYTES;
@@ -177,8 +182,13 @@ __global__ void __launch_bounds__(AT_THREADS, (DA == 1 ? 2 : 1)) attn_kernel(con
                     const uint64_t dp = make_kmajor_sw128_desc(sp_addr + a * (AT_BQ * 128));
                     const uint64_t dv = make_kmajor_sw128_desc(sv + a * (DP * 128));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_f16(tmem_base + BKV, dp + 2 * k, dv + 2 * k, idesc_o, (j > 0 || a > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t acc = (j > 0 || a > 0 || k > 0) ? 1u : 0u;
+                        if constexpr (PTS)   // A = P from tensor memory: K step (a*4 + k) of 16 elements = 8 packed columns
+                            umma_f16_ts(tmem_base + BKV, tmem_base + BKV + DP + (a * 4 + k) * 8, dv + 2 * k, idesc_o, acc);
+                        else
+                            umma_f16(tmem_base + BKV, dp + 2 * k, dv + 2 * k, idesc_o, acc);
+                    }
                 }
                 umma_commit(o_done);
                 umma_commit(&v_empty[st]);
@@ -249,12 +259,16 @@ __global__ void __launch_bounds__(AT_THREADS, (DA == 1 ? 2 : 1)) attn_kernel(con
                     pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
                 }
                 const int cabs = hf * HC + c;      // column inside the KV block
-                uint8_t* prow = sP + (cabs >> 6) * (AT_BQ * 128);
+                if constexpr (PTS) {
+                    tmem_st16(lane_addr + BKV + DP + (cabs >> 1), pk);   // 32 fp16 = 16 packed columns of this thread's lane
+                } else {
+                    uint8_t* prow = sP + (cabs >> 6) * (AT_BQ * 128);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t chunk = ((cabs & 63) >> 3) + u;
-                    *reinterpret_cast<uint4*>(prow + sw128_offset(r, chunk)) =
-                        make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t chunk = ((cabs & 63) >> 3) + u;
+                        *reinterpret_cast<uint4*>(prow + sw128_offset(r, chunk)) =
+                            make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+                    }
                 }
             }
             // rescale this thread's half of the running O accumulator (TMEM) when any row of the warp moved its max
@@ -275,7 +289,8 @@ __global__ void __launch_bounds__(AT_THREADS, (DA == 1 ? 2 : 1)) attn_kernel(con
             }
             l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
             m_run = m_new;
-            fence_proxy_async_smem();  // P stores -> visible to the UMMA (async proxy)
+            if constexpr (PTS) tmem_st_wait();   // P (and a rescaled O) have landed in tensor memory
+            else fence_proxy_async_smem();       // P stores -> visible to the UMMA (async proxy)
             tc_fence_before();
             mbar_arrive(p_full);
         };
@@ -354,12 +369,17 @@ static int encode_2d(CUtensorMap* m, const __half* ptr, long cols, long rows, lo
     return 0;
 }
 
-static size_t attn_smem_bytes(int da, int bkv) {
+static bool attn_p_in_tmem(int dp) {
+    static const bool off = getenv("B2_NO_ATTN_PTS") != nullptr;   // debug: P through shared memory again (round-1 data path)
+    return dp == 64 && !off;
+}
+static size_t attn_smem_bytes(int da, int bkv, bool pts) {
     const size_t q = (size_t)da * AT_BQ * 128;
     const size_t k = (size_t)da * bkv * 128;
     const size_t v = (size_t)(bkv / 64) * da * 64 * 128;
     const size_t pb = (size_t)(bkv / 64) * AT_BQ * 128;
-    return q + AT_STAGES * (k + v) + pb + 256 + 512;   // + barriers + pair-exchange scratch (2 CTAs of <1,128> still fit an SM)
+    // + barriers + pair-exchange scratch (2 CTAs of <1,128> still fit an SM); P in tensor memory: a third K/V stage instead of P
+    return q + (pts ? (AT_STAGES + 1) * (k + v) : AT_STAGES * (k + v) + pb) + 256 + 512;
 }
 
 int attn_plan(const AttnDesc& d, AttnPlan* plan) {
@@ -378,7 +398,7 @@ int attn_plan(const AttnDesc& d, AttnPlan* plan) {
     if (encode_2d(&plan->tmk, d.k, (long)d.heads * d.dp, d.k_rows, d.ldk, 64, bkv, "k")) return -1;
     if (encode_2d(&plan->tmv, d.vt, d.vt_cols, (long)d.heads * d.dp, d.ldvt, 64, d.dp, "vt")) return -1;
     plan->grid = dim3((d.sq + AT_BQ - 1) / AT_BQ, d.heads, d.nb);
-    plan->smem = attn_smem_bytes(d.dp / 64, bkv);
+    plan->smem = attn_smem_bytes(d.dp / 64, bkv, attn_p_in_tmem(d.dp));
     return 0;
 }
 
@@ -386,6 +406,7 @@ int attn_init() {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e1 = cudaFuncSetAttribute(attn_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(attn_kernel<1, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaError_t e2 = cudaFuncSetAttribute(attn_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaError_t e3 = cudaFuncSetAttribute(attn_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
@@ -407,7 +428,8 @@ int attn_launch(const AttnPlan& plan, cudaStream_t s) {
     p.k_bstride = d.k_bstride; p.vt_bstride = d.vt_bstride;
     p.scale_log2 = (float)(1.4426950408889634 / sqrt((double)d.d_real));
     cudaError_t e;
-    if (d.dp == 64) e = launch_k(attn_kernel<1, 128>, plan.grid, dim3(AT_THREADS), plan.smem, s, 1, p);
+    if (attn_p_in_tmem(d.dp)) e = launch_k(attn_kernel<1, 128, true>, plan.grid, dim3(AT_THREADS), plan.smem, s, 1, p);
+    else if (d.dp == 64) e = launch_k(attn_kernel<1, 128>, plan.grid, dim3(AT_THREADS), plan.smem, s, 1, p);
     else if (d.dp == 128) e = launch_k(attn_kernel<2, 128>, plan.grid, dim3(AT_THREADS), plan.smem, s, 1, p);
     else e = launch_k(attn_kernel<3, 64>, plan.grid, dim3(AT_THREADS), plan.smem, s, 1, p);
     if (e != cudaSuccess) {

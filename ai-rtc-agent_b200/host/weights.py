@@ -106,15 +106,25 @@ def fuse_lora(unet_sd: Dict[str, torch.Tensor], lora_sd: Dict[str, torch.Tensor]
     return fused
 
 
+def layout_variant(batch: int, height: int, width: int) -> str:
+    """The packed layouts are the same for every batch / resolution except one case: with a stream batch > 1, attention levels
+    whose token count is not a multiple of 8 keep separate q/k and v matrices (per-image V^T padding) instead of the fused,
+    LayerNorm-folded [q|k|v] -- a different set of packed tensors, hence a different blob."""
+    if batch <= 1:
+        return ""
+    ragged = [i for i in range(4) if ((height // 8) >> i) * ((width // 8) >> i) % 8 != 0]
+    return "ragged" + "".join(str(i) for i in ragged) if ragged else ""
+
+
 def packed_blob_path(engine_dir, model_id_or_path: str, arch_name: str, use_lcm_lora: bool, lcm_lora_id: Optional[str],
-                     lora_dict: Optional[Dict[str, float]], vae_id: Optional[str], synthetic: bool) -> str:
+                     lora_dict: Optional[Dict[str, float]], vae_id: Optional[str], synthetic: bool, variant: str = "") -> str:
     """Where the packed-weight blob of this model lives: `<engine_dir>/engines--<model>/b2sd-<arch>-<recipe hash>.b2pack`,
     the directory naming of the reference's TensorRT cache (lib/wrapper.py:593, `engines--` + model id with / -> --).
     The hash covers everything that changes the weight VALUES (LoRAs and their scales, LCM-LoRA, VAE, synthetic seed), not
     batch / resolution / prompt (the blob does not depend on them, unlike the reference's static-shape engines)."""
     import hashlib
     import json
-    recipe = {"lcm": bool(use_lcm_lora), "lcm_id": lcm_lora_id, "vae": vae_id, "synthetic": bool(synthetic),
+    recipe = {"lcm": bool(use_lcm_lora), "lcm_id": lcm_lora_id, "vae": vae_id, "synthetic": bool(synthetic), "layout": variant,
               "loras": sorted((str(k), float(v)) for k, v in (lora_dict or {}).items())}
     for path, _ in recipe["loras"]:
         if os.path.exists(path):   # a replaced LoRA file must not hit the old blob

@@ -153,7 +153,8 @@ class StreamDiffusionWrapper:
             (have_ckpt or mode == "synthetic")
         if use_cache:
             blob = W.packed_blob_path(self.engine_dir, model_id_or_path, arch.name, use_lcm_lora and not self.sd_turbo, lcm_lora_id,
-                                      lora_dict, vae_id, synthetic=not have_ckpt)
+                                      lora_dict, vae_id, synthetic=not have_ckpt,
+                                      variant=W.layout_variant(self.batch_size, self.height, self.width))
         encoder = make_prompt_encoder(repo if have_ckpt else None, arch.cross_attention_dim, self.device, allow_synthetic=synthetic_ok)
         if blob is not None and os.path.exists(blob) and (have_ckpt or synthetic_ok):
             try:

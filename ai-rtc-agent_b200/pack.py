@@ -55,7 +55,8 @@ def main(argv=None) -> int:
     repo = W.find_local_repo(args.model_id)
     have_ckpt = repo is not None and os.path.isdir(os.path.join(repo, "unet"))
     blob = W.packed_blob_path(args.engine_dir, args.model_id, A.arch_for(args.model_id).name, not args.no_lcm_lora and not turbo,
-                              args.lcm_lora_id, loras, args.vae_id, synthetic=not have_ckpt)
+                              args.lcm_lora_id, loras, args.vae_id, synthetic=not have_ckpt,
+                              variant=W.layout_variant(len(t_index_list), args.height, args.width))
     if not have_ckpt:
         if not (os.getenv(W.ALLOW_SYNTHETIC_ENV) or args.model_id.startswith(("tiny", "synthetic"))):
             raise SystemExit(f"pack: no checkpoint for '{args.model_id}' on disk (set {W.ALLOW_SYNTHETIC_ENV}=1 to pack seeded synthetic weights)")

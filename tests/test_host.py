@@ -278,6 +278,11 @@ def test_packed_blob_path_follows_the_reference_cache_naming():
     c = W.packed_blob_path("./models/engines", "lykon/dreamshaper-8", "sd15", True, None, None, None, False)
     assert os.path.dirname(a) == os.path.join("./models/engines", "engines--lykon--dreamshaper-8")   # lib/wrapper.py:593
     assert a.endswith(".b2pack") and len({a, b, c}) == 3, "the LoRA recipe is part of the key"
+    # batch / resolution do not change the blob, except stream batches whose attention levels have ragged token counts
+    assert W.layout_variant(1, 512, 512) == W.layout_variant(4, 512, 512) == W.layout_variant(4, 768, 768) == ""
+    assert W.layout_variant(4, 128, 128) == "ragged3" and W.layout_variant(1, 128, 128) == ""
+    d = W.packed_blob_path("./e", "m", "sd15", True, None, None, None, False, variant=W.layout_variant(4, 128, 128))
+    assert d != W.packed_blob_path("./e", "m", "sd15", True, None, None, None, False)
 
 
 def test_pack_cli_argument_parsing():
