@@ -9,7 +9,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <chrono>
 #include <functional>
+#include <thread>
 #include <map>
 #include <memory>
 #include <string>
@@ -1639,6 +1642,15 @@ int b2sd_profile(b2sd_handle h, const void* frame_in, int in_h, int in_w, void* 
     return 0;
 }
 
+// Start gate for concurrent b2sd_profile_kind calls (one host thread per lane): every call finishes its capture / instantiation /
+// warm-up replays, then waits here until all participants have arrived, so that the TIMED replays of the lanes really overlap.
+static std::atomic<int> g_gate_expected{0}, g_gate_arrived{0};
+int b2sd_profile_gate(int participants) {
+    g_gate_arrived.store(0);
+    g_gate_expected.store(participants > 1 ? participants : 0);
+    return 0;
+}
+
 // Device time of one launch class inside a CUDA graph: every frame-program launch whose label starts with `kind`
 // ("igemm", "attn", "groupnorm", ...) is captured, in program order, into its own graph (same PDL edges, same buffers,
 // same weight streaming as the frame graph) and that graph is replayed `iters` times between two events.
@@ -1679,6 +1691,13 @@ int b2sd_profile_kind(b2sd_handle h, const char* kind, int iters, double* ms_per
     CUDA_OK(cudaEventCreate(&e0));
     CUDA_OK(cudaEventCreate(&e1));
     for (int i = 0; i < 3; ++i) CUDA_OK(cudaGraphLaunch(ge, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    if (const int expect = g_gate_expected.load()) {   // concurrent measurement: start the timed replays together
+        g_gate_arrived.fetch_add(1);
+        const auto t0 = std::chrono::steady_clock::now();
+        while (g_gate_arrived.load() < expect && std::chrono::steady_clock::now() - t0 < std::chrono::seconds(20))
+            std::this_thread::sleep_for(std::chrono::microseconds(50));
+    }
     CUDA_OK(cudaEventRecord(e0, s));
     for (int i = 0; i < iters; ++i) CUDA_OK(cudaGraphLaunch(ge, s));
     CUDA_OK(cudaEventRecord(e1, s));

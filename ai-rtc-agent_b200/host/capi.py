@@ -124,6 +124,8 @@ def lib() -> C.CDLL:
         _lib.b2sd_profile.restype = C.c_int
         _lib.b2sd_profile_kind.argtypes = [vp, C.c_char_p, ci, C.POINTER(C.c_double), C.POINTER(ci), C.POINTER(C.c_double), vp]
         _lib.b2sd_profile_kind.restype = C.c_int
+        _lib.b2sd_profile_gate.argtypes = [ci]
+        _lib.b2sd_profile_gate.restype = C.c_int
         for name in ("create", "create_lane", "destroy", "load_tensor", "prepare", "export_packed", "import_packed", "set_prompt_embeds", "set_timesteps", "step",
                      "step_ex", "get_tensor", "launches_per_step"):
             getattr(_lib, "b2sd_" + name).restype = C.c_int

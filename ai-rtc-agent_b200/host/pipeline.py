@@ -25,7 +25,7 @@ DEFAULT_PROMPT = "fireworks in the night sky"
 DEFAULT_T_INDEX_LIST = [18, 26, 35, 45]
 DEFAULT_NUM_INFERENCE_STEPS = 50
 DEFAULT_GUIDANCE_SCALE = 0.0
-DEFAULT_LANES_ONE_STEP = 4    # frames in flight for a 1-step stream batch (measured: 1 -> 232, 2 -> 315, 4 -> 397, 6 -> 413 fps)
+DEFAULT_LANES_ONE_STEP = 6    # frames in flight for a 1-step stream batch (measured: 1 -> 241, 2 -> 331, 4 -> 423, 6 -> 443, 8 -> 441 fps; p50 4.2 / 6.1 / 9.6 / 13.6 / 18.4 ms)
 DEFAULT_LANES_STATEFUL = 2    # T > 1: stage pipelining over two lanes that share the stream-batch state
 
 

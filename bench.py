@@ -455,8 +455,10 @@ def main_gpu(args):
         """The launches of one class of ALL lanes replayed at the same time (one host thread + CUDA stream per lane, like the
         frames in flight of the timed region): aggregate algorithmic FLOP/s of that kernel under the conditions it really runs in."""
         import threading
+        from ai_rtc_agent_b200.host import capi
         res = [None] * lanes
         gate = threading.Barrier(lanes)
+        capi.lib().b2sd_profile_gate(lanes)   # the lanes' timed replays start together (after capture / warm-up of all of them)
 
         def work(k):
             torch.cuda.set_device(dev)
@@ -469,6 +471,7 @@ def main_gpu(args):
             t.start()
         for t in th:
             t.join()
+        capi.lib().b2sd_profile_gate(0)
         ms = sum(r["ms"] for r in res) / lanes
         return {"ms": ms, "flops": sum(r["flops"] for r in res), "launches": res[0]["launches"]}
 

@@ -237,6 +237,9 @@ int b2sd_profile(b2sd_handle h, const void* frame_in, int in_h, int in_w, void* 
 int b2sd_profile_kind(b2sd_handle h, const char* kind, int iters, double* ms_per_replay, int* launches, double* flops,
                       void* stream);
 /* number of kernel launches (graph nodes) in one b2sd_step */
+/* Concurrent use of b2sd_profile_kind (one host thread and CUDA stream per lane): after b2sd_profile_gate(n) the next n calls
+ * wait for each other between their warm-up and their timed replays, so the timed regions overlap.  0 / 1 switches it off. */
+int b2sd_profile_gate(int participants);
 int b2sd_launches_per_step(b2sd_handle h);
 /* Stage pipelining of ONE stateful stream (stream batch T > 1, where frame n+1 needs frame n's latent buffer and lanes cannot
  * simply alternate): `lane` shares `owner`'s stream-batch state; the frame program of each is cut into TAESD encoder body |
