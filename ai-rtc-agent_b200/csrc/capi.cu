@@ -34,6 +34,7 @@ static void to_igemm_desc(const b2sd_igemm_desc* d, IgemmDesc& g) {
     g.Nb = d->nb; g.Ho = d->ho; g.Wo = d->wo;
     g.BN = d->bn;
     g.swap = d->swap;
+    g.pair = (d->flags & B2SD_IG_PAIR) ? 1 : 0;
     g.splits = d->splits;
     g.partial = nullptr;
     g.dbg_ts = reinterpret_cast<unsigned long long*>(d->partial);  // op-level entry: `partial` doubles as the debug timeline buffer

@@ -117,7 +117,27 @@ struct Op {
 // Tile / split-K policy of the frame program (batch-1 driven; derived from the cold-weight sweep in
 // profiles/r01_tile_sweep.md, not from a model).  Fills `plan` for the chosen (BN, splits, orientation).
 // allow_swap: the caller is a UNet contraction (never TAESD / V^T / GEGLU).  Host-only: works in igemm dry-run mode.
+static int igemm_autotile_single(IgemmDesc d, bool allow_swap, IgemmPlan* plan_out);
+
+// Tile policy + CTA pairs: the single-CTA policy picks orientation, N tile and split-K; where the result has at least two M tiles
+// (normal orientation, N tile a multiple of 32, split-K <= 4) the same tiles are launched as CTA pairs (igemm_pair_kernel), which
+// halves the weight bytes every SM stages and reads per MMA.  B2_PAIR=0 switches the pairs off.
 int igemm_autotile(IgemmDesc d, bool allow_swap, IgemmPlan* plan_out) {
+    TRY(igemm_autotile_single(d, allow_swap, plan_out));
+    static const char* pair_env = getenv("B2_PAIR");
+    const int pair_mode = pair_env ? atoi(pair_env) : 0;
+    const IgemmPlan& pl = *plan_out;
+    const int m_tiles = pl.p.tiles_w * pl.p.tiles_h * pl.p.tiles_n;
+    if (pair_mode <= 0 || pl.p.swap || m_tiles < 2 || (pl.p.BN % 32) != 0 || pl.splits > 4) return 0;
+    if (pair_mode == 2 && pl.p.total_kb < 20) return 0;   // K-heavy contractions only (the mainloop must dominate)
+    d.swap = 0; d.BN = pl.p.BN; d.splits = pl.splits; d.partial = nullptr; d.pair = 1;
+    IgemmPlan paired;
+    if (igemm_plan(d, &paired)) return 0;   // keep the single-CTA plan
+    *plan_out = paired;
+    return 0;
+}
+
+static int igemm_autotile_single(IgemmDesc d, bool allow_swap, IgemmPlan* plan_out) {
     IgemmPlan& plan = *plan_out;
     const bool geglu = (d.epi.flags & IG_GEGLU) != 0;
     const int n_gemm = geglu ? 2 * d.epi.n_valid : d.epi.n_valid;
@@ -469,7 +489,7 @@ struct b2sd_engine {
         char label[256];
         snprintf(label, sizeof(label), "igemm %s rows=%ld n=%d kb=%d bn=%d splits=%d grid=%u,%u,%u %s", cur.c_str(),
                  plan.rows_total, d.epi.n_valid, plan.p.total_kb, plan.p.BN, plan.splits, plan.grid.x, plan.grid.y,
-                 plan.grid.z, plan.p.swap ? "swapped" : "taps");
+                 plan.grid.z, plan.p.swap ? "swapped" : (plan.pair ? "pairs" : "taps"));
         push_igemm(dst, plan, label, 2.0 * (double)plan.rows_total * n_gemm * plan.p.total_kb * IG_BK);
         return 0;
     }

@@ -116,8 +116,9 @@ __device__ __forceinline__ void swap_store_chunk(const IgemmParams& p, const Swa
 // Cluster split-K: sum one 16-column (4 x float4) strip of accumulator row `row` over the K slices held in the peers'
 // shared memory.  All loads of up to four slices are in flight together (a dependent chain of DSMEM round trips was
 // the dominant cost of the reduction); the summation order is fixed => bit-reproducible.
+// (pair launches: cluster dims (2,1,splits), the K slice s of this CTA's M half lives in cluster rank 2*s + rank_add)
 template <int SPL>
-__device__ __forceinline__ void splitk_sum16(uint32_t stg_local, int cc, int row, float (&acc)[16]) {
+__device__ __forceinline__ void splitk_sum16(uint32_t stg_local, int cc, int row, float (&acc)[16], int rank_mul = 1, int rank_add = 0) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0.f;
     constexpr int G = SPL < 4 ? SPL : 4;
@@ -126,7 +127,7 @@ __device__ __forceinline__ void splitk_sum16(uint32_t stg_local, int cc, int row
         float4 v[G][4];
 #pragma unroll
         for (int s = 0; s < G; ++s) {
-            const uint32_t peer = dsmem_map(stg_local, (uint32_t)(s0 + s));
+            const uint32_t peer = dsmem_map(stg_local, (uint32_t)((s0 + s) * rank_mul + rank_add));
 #pragma unroll
             for (int i = 0; i < 4; ++i) v[s][i] = dsmem_ld_f4(peer + (uint32_t)(((cc * 4 + i) * IG_BM + row) * 16));
         }
@@ -140,18 +141,29 @@ __device__ __forceinline__ void splitk_sum16(uint32_t stg_local, int cc, int row
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant__ IgemmParams p) {
+// PAIR: the CTAs (2j, 2j+1) of grid.x form a CTA pair (cluster dims (2,1,splits)) that computes two neighbouring M tiles with
+// ONE tcgen05.mma.cta_group::2 stream of M = 256: each CTA loads its own 128 pixel rows and half of the weight tile, the even
+// CTA issues the MMAs for both, every CTA drains its own 128 accumulator rows.  Barrier plumbing across the pair: the odd
+// CTA's (otherwise idle) MMA warp relays "my operands of this stage have landed" to the leader; ring slots are released in both
+// CTAs by a multicast commit; both epilogues arrive on the leader's accumulator-drained barrier.
+template <bool PAIR>
+__device__ __forceinline__ void igemm_body(const IgemmParams& p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~static_cast<uintptr_t>(1023));
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t stage_bytes = IG_BM * IG_BK * 2 + (uint32_t)p.BN * IG_BK * 2;
+    const uint32_t stage_bytes = IG_BM * IG_BK * 2 + (uint32_t)(PAIR ? p.BN / 2 : p.BN) * IG_BK * 2;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.num_stages * stage_bytes);
     uint64_t* empty_bar = full_bar + IG_MAX_STAGES;
     uint64_t* tmem_full_bar = empty_bar + IG_MAX_STAGES;   // [2] accumulator ready   (MMA -> epilogue)
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;          // [2] accumulator drained (epilogue -> MMA)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint64_t* peer_full = full_bar + 32;                   // [stages] (pair leader) the peer CTA's operands have landed
+    const int cr = PAIR ? (int)(blockIdx.x & 1) : 0;       // rank inside the CTA pair (0 = leader)
+    const int mt_first = PAIR ? (int)(blockIdx.x & ~1u) + cr : (int)blockIdx.x;   // first M tile of this CTA ...
+    const int mt_step = (int)gridDim.x;                    // ... and the stride of a persistent launch (even for pairs)
+    const int mt_guard = PAIR ? cr : 0;                    // pairs iterate together: the loop bound looks at the leader's tile
 
     // Persistent over M tiles: CTA x handles tiles x, x + gridDim.x, ... with two TMEM accumulators, so the epilogue of
     // tile i overlaps the mainloop of tile i+1 and the prologue (barriers, TMEM, descriptors) is paid once per CTA.
@@ -168,16 +180,23 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
         for (int s = 0; s < p.num_stages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
+            if (PAIR) mbar_init(&peer_full[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full_bar[s], 1);
-            mbar_init(&tmem_empty_bar[s], 128);
+            mbar_init(&tmem_empty_bar[s], PAIR ? 256 : 128);
         }
         fence_mbar_init();
     }
+    if (PAIR) cluster_sync_all();   // the peer's barriers exist before anything arrives on them; both CTAs are resident
     if (warp == 1) {
-        tmem_alloc(tmem_slot, p.tmem_cols);
-        tmem_relinquish();
+        if (PAIR) {
+            tmem_alloc_2cta(tmem_slot, p.tmem_cols);
+            tmem_relinquish_2cta();
+        } else {
+            tmem_alloc(tmem_slot, p.tmem_cols);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -194,9 +213,9 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
             // ===== TMA producer =====
             int stage = 0;
             uint32_t phase = 0;
-            for (int mt = blockIdx.x; mt < num_mtiles; mt += gridDim.x) {
+            for (int mt = mt_first; mt - mt_guard < num_mtiles; mt += mt_step) {
                 const int w0 = (mt % p.tiles_w) * p.tw, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
-                const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
+                const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;   // (odd tile count: the last pair's second tile lies outside, TMA zero-fills)
                 int seg = 0, base = 0;
                 while (seg < p.nseg - 1 && kb_begin >= base + p.seg_ntap[seg] * p.seg_cblocks[seg]) {
                     base += p.seg_ntap[seg] * p.seg_cblocks[seg];
@@ -224,7 +243,8 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                     // normal: pixels -> A (M side), weights -> B.  swapped: weights (128 output channels) -> A, pixels -> B
                     tma_load_4d(p.swap ? sb : sa, &p.tmA[seg], &full_bar[stage], p.seg_c0[seg] + cb * IG_BK,
                                 w0 * p.stride + dx, h0 * p.stride + dy, n0);
-                    tma_load_2d(p.swap ? sa : sb, &p.tmB, &full_bar[stage], kb * IG_BK, ntile * (p.swap ? IG_BM : p.BN));
+                    tma_load_2d(p.swap ? sa : sb, &p.tmB, &full_bar[stage], kb * IG_BK,
+                                ntile * (p.swap ? IG_BM : p.BN) + (PAIR ? cr * (p.BN / 2) : 0));
                     B2_TS(if (ts && mt == (int)blockIdx.x && kb == kb_begin) ts[2] = globaltimer_ns();)
                     if (++cb == p.seg_cblocks[seg]) {
                         cb = 0;
@@ -240,23 +260,43 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                 }
             }
         }
+    } else if (warp == 1 && PAIR && cr == 1) {
+        // ===== pair follower: relay "operands of this stage have landed in MY shared memory" to the leader =====
+        const uint32_t leader_peer_full = dsmem_map(smem_u32(peer_full), cluster_ctarank() & ~1u);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int mt = mt_first; mt - mt_guard < num_mtiles; mt += mt_step) {
+            for (int kb = kb_begin; kb < kb_end; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                if (elect_one()) mbar_arrive_remote(leader_peer_full + (uint32_t)stage * 8u);
+                __syncwarp();
+                if (++stage == p.num_stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         // The whole warp walks the loop (warp-uniform control flow keeps descriptors in uniform registers, which is
         // what UTCHMMA consumes); one elected lane issues.  A divergent single-thread loop issues ~2.5x slower
         // (probe.cu / tools/probe_rowshift.py).
-        const uint32_t idesc = make_idesc_f16(IG_BM, p.BN);
+        const uint32_t idesc = make_idesc_f16(PAIR ? 2 * IG_BM : IG_BM, p.BN);
         const uint32_t smem_base = smem_u32(smem);
+        [[maybe_unused]] const uint16_t pair_mask = (uint16_t)(3u << (cluster_ctarank() & ~1u));
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
-        for (int mt = blockIdx.x; mt < num_mtiles; mt += gridDim.x, ++it) {
+        for (int mt = mt_first; mt < num_mtiles; mt += mt_step, ++it) {
             const int buf = it & 1;
-            mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+            // epilogue has drained this accumulator (pairs: both CTAs' epilogues arrive here)
+            if (PAIR) mbar_wait_cluster(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);
+            else mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)buf * acc_stride;
             for (int kb = kb_begin; kb < kb_end; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
+                if (PAIR) mbar_wait_cluster(&peer_full[stage], phase);
                 tc_fence_after();
                 B2_TS(if (ts && it == 0 && kb == kb_begin && lane == 0) ts[3] = globaltimer_ns();)
                 const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
@@ -270,11 +310,19 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
 #endif
                 if (elect_one()) {
                     // +32 B per UMMA_K inside the 128 B swizzle row => +2 in the (addr>>4) field
-                    umma_f16(tacc, da, db, idesc, acc0);
-                    umma_f16(tacc, da + 2, db + 2, idesc, 1u);
-                    umma_f16(tacc, da + 4, db + 4, idesc, 1u);
-                    umma_f16(tacc, da + 6, db + 6, idesc, 1u);
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    if (PAIR) {
+                        umma_f16_2cta(tacc, da, db, idesc, acc0);
+                        umma_f16_2cta(tacc, da + 2, db + 2, idesc, 1u);
+                        umma_f16_2cta(tacc, da + 4, db + 4, idesc, 1u);
+                        umma_f16_2cta(tacc, da + 6, db + 6, idesc, 1u);
+                        umma_commit_2cta(&empty_bar[stage], pair_mask);  // frees the slot in BOTH CTAs
+                    } else {
+                        umma_f16(tacc, da, db, idesc, acc0);
+                        umma_f16(tacc, da + 2, db + 2, idesc, 1u);
+                        umma_f16(tacc, da + 4, db + 4, idesc, 1u);
+                        umma_f16(tacc, da + 6, db + 6, idesc, 1u);
+                        umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    }
                 }
                 __syncwarp();
                 if (++stage == p.num_stages) {
@@ -282,7 +330,10 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                     phase ^= 1;
                 }
             }
-            if (elect_one()) umma_commit(&tmem_full_bar[buf]);
+            if (elect_one()) {
+                if (PAIR) umma_commit_2cta(&tmem_full_bar[buf], pair_mask);
+                else umma_commit(&tmem_full_bar[buf]);
+            }
             __syncwarp();
             B2_TS(if (ts && it == 0 && lane == 0) ts[4] = globaltimer_ns();)
         }
@@ -306,8 +357,9 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
             }
             epi_bar_sync();
         }
+        [[maybe_unused]] const uint32_t leader_tmem_empty = PAIR ? dsmem_map(smem_u32(tmem_empty_bar), cluster_ctarank() & ~1u) : 0u;
         int it = 0;
-        for (int mt = blockIdx.x; mt < num_mtiles; mt += gridDim.x, ++it) {
+        for (int mt = mt_first; mt - mt_guard < num_mtiles; mt += mt_step, ++it) {
             const int buf = it & 1;
             const uint32_t par = (it >> 1) & 1;
             const int w0 = (mt % p.tiles_w) * p.tw, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
@@ -415,7 +467,8 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
             }
             // accumulator `buf` is drained: the MMA warp may start the tile after next into it
             tc_fence_before();
-            mbar_arrive(&tmem_empty_bar[buf]);
+            if (PAIR && cr == 1) mbar_arrive_remote(leader_tmem_empty + (uint32_t)buf * 8u);
+            else mbar_arrive(&tmem_empty_bar[buf]);
             B2_TS(if (ts && it == 0 && threadIdx.x == 64) ts[5] = globaltimer_ns();)
         }
     }
@@ -427,6 +480,7 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
         const int w0 = (mt % p.tiles_w) * p.tw, h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
         const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
         const int splits = (int)gridDim.z;
+        const int rk_mul = PAIR ? 2 : 1, rk_add = cr;   // cluster rank of K slice s (same M half) = s * rk_mul + rk_add
         cluster_sync_all();  // all partial tiles are in place (release/acquire over the cluster)
         B2_TS(if (ts && threadIdx.x == 64) ts[6] = globaltimer_ns();)   // split launches: [5] staged, [6] cluster barrier passed, [7] reduced
         if (warp >= 2 && p.swap) {
@@ -474,7 +528,7 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                 epi_bar_sync();
             }
         } else if (warp >= 2) {
-            const int rank = (int)cluster_ctarank();
+            const int rank = (int)cluster_ctarank() / rk_mul;
             const int rows_per = IG_BM / splits;          // splits in {2,4,8}
             const int t = threadIdx.x - 64;               // 0..127
             const int chunks = p.BN >> 4;
@@ -488,9 +542,9 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
                 const bool ok = (ni < p.tn) && (n < p.Nb) && (h < p.Ho) && (w < p.Wo);
                 float acc[16];
                 switch (splits) {
-                    case 2: splitk_sum16<2>(stg_local, cc, r, acc); break;
-                    case 4: splitk_sum16<4>(stg_local, cc, r, acc); break;
-                    default: splitk_sum16<8>(stg_local, cc, r, acc); break;
+                    case 2: splitk_sum16<2>(stg_local, cc, r, acc, rk_mul, rk_add); break;
+                    case 4: splitk_sum16<4>(stg_local, cc, r, acc, rk_mul, rk_add); break;
+                    default: splitk_sum16<8>(stg_local, cc, r, acc, rk_mul, rk_add); break;
                 }
                 if (ok) {
                     const long orow = ((long)n * p.Ho + h) * p.Wo + w;
@@ -504,10 +558,17 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
         cluster_sync_all();  // nobody may exit while a peer still reads its shared memory
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+    if (PAIR) cluster_sync_all();   // both CTAs are done with the pair's tensor memory and with each other's barriers
+    else __syncthreads();
+    if (warp == 1) {
+        if (PAIR) tmem_dealloc_2cta(tmem_base, p.tmem_cols);
+        else tmem_dealloc(tmem_base, p.tmem_cols);
+    }
     B2_TS(if (ts && threadIdx.x == 32 && !(p.epi.flags & IG_SPLITK)) ts[7] = globaltimer_ns();)
 }
+
+__global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant__ IgemmParams p) { igemm_body<false>(p); }
+__global__ void __launch_bounds__(IG_THREADS) igemm_pair_kernel(const __grid_constant__ IgemmParams p) { igemm_body<true>(p); }
 
 // ------------------------------------------------------------------------------------------
 // host side
@@ -705,6 +766,11 @@ int igemm_plan(const IgemmDesc& d, IgemmPlan* plan) {
         b2_set_error("igemm: unsupported BN %d (n %d)", BN, n_gemm);
         return -1;
     }
+    const bool pair = d.pair != 0;
+    if (pair && BN % 32 != 0) {
+        b2_set_error("igemm(pair): BN %d must be a multiple of 32", BN);
+        return -1;
+    }
     p.BN = BN;
     { static const char* dm = getenv("B2_DBG_MODE"); p.dbg_mode = dm ? atoi(dm) : 0; }
     const int n_tiles = (n_gemm + BN - 1) / BN;
@@ -766,12 +832,14 @@ int igemm_plan(const IgemmDesc& d, IgemmPlan* plan) {
         b2_set_error("igemm: weight ld %d < K %d or misaligned", d.w_ld, total_kb * IG_BK);
         return -1;
     }
-    if (encode_w_map(&p.tmB, d.w, d.w_rows, d.w_ld, BN)) return -1;
+    const int b_rows = pair ? BN / 2 : BN;   // weight rows one CTA stages per K-block
+    if (encode_w_map(&p.tmB, d.w, d.w_rows, d.w_ld, b_rows)) return -1;
     p.a_bytes = (uint32_t)(tw * th * tn) * IG_BK * 2;
-    p.b_bytes = (uint32_t)BN * IG_BK * 2;
+    p.b_bytes = (uint32_t)b_rows * IG_BK * 2;
     // ---- split-K
     int splits = d.splits < 1 ? 1 : d.splits;
     if (splits > total_kb) splits = total_kb;
+    if (pair && splits > 4) splits = 4;   // cluster = 2 x splits CTAs, portable limit 8
     if (splits >= 8) splits = 8;        // portable cluster size; power of two so rows divide evenly
     else if (splits >= 4) splits = 4;
     else if (splits >= 2) splits = 2;
@@ -795,7 +863,7 @@ int igemm_plan(const IgemmDesc& d, IgemmPlan* plan) {
     // ---- pipeline depth / smem
     // one K-block (64 channels of one tap) per pipeline stage: packing several per stage was measured slower (shallower
     // prefetch, longer MMA issue code)
-    const size_t stage_bytes = (size_t)IG_BM * IG_BK * 2 + (size_t)BN * IG_BK * 2;
+    const size_t stage_bytes = (size_t)IG_BM * IG_BK * 2 + (size_t)b_rows * IG_BK * 2;
     // TMA latency under load is ~1.3 us (tools/timeline.py): throughput per SM = bytes in flight / latency.  With at
     // most ~1 CTA per SM take the whole shared memory for the ring; with many CTAs keep two co-resident instead.
     static const char* pc_env = getenv("B2_PERSIST_CTAS");   // tuning: resident CTAs of a persistent launch (default 2 per SM)
@@ -840,11 +908,13 @@ int igemm_plan(const IgemmDesc& d, IgemmPlan* plan) {
         if (grid_x > m_tiles) grid_x = m_tiles;
         p.acc_bufs = 2;
     }
+    if (pair) grid_x = (grid_x + 1) & ~1;   // CTAs (2j, 2j+1) of x are a pair; an odd tile count leaves one masked tile
     uint32_t cols = 32;
     while (cols < (uint32_t)(BN * p.acc_bufs)) cols <<= 1;
     p.tmem_cols = cols;
     plan->grid = dim3(grid_x, n_tiles, splits);
-    plan->mode = 0;
+    plan->mode = pair ? 1 : 0;
+    plan->pair = pair ? 1 : 0;
     return 0;
 }
 
@@ -862,6 +932,11 @@ int igemm_init() {
             b2_set_error("cudaFuncSetAttribute(igemm): %s", cudaGetErrorString(e));
             return -1;
         }
+        e = cudaFuncSetAttribute(igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) {
+            b2_set_error("cudaFuncSetAttribute(igemm pair): %s", cudaGetErrorString(e));
+            return -1;
+        }
         if (!get_encode()) return -1;
         attr_set = true;
     }
@@ -871,7 +946,8 @@ int igemm_init() {
 int igemm_launch(const IgemmPlan& plan, cudaStream_t stream) {
     if (igemm_init()) return -1;
     const int cz = plan.splits > 1 ? plan.splits : 1;
-    cudaError_t e = launch_k(igemm_kernel, plan.grid, dim3(IG_THREADS), plan.smem, stream, cz, plan.p);
+    cudaError_t e = plan.pair ? launch_kc(igemm_pair_kernel, plan.grid, dim3(IG_THREADS), plan.smem, stream, 2, cz, plan.p)
+                              : launch_k(igemm_kernel, plan.grid, dim3(IG_THREADS), plan.smem, stream, cz, plan.p);
     if (e != cudaSuccess) {
         b2_set_error("igemm launch: %s", cudaGetErrorString(e));
         return -1;

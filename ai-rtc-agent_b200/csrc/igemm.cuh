@@ -103,6 +103,8 @@ struct IgemmDesc {
     int splits;       // 0/1 = none
     int ring_kb;      // operand ring budget in KB, 0 = auto (200 when the launch has <= 1 CTA per SM, else 100)
     int max_splits;   // cap of the split-K factor chosen by igemm_autotile, 0 = 8
+    int pair;         // 1 = CTA pairs (tcgen05.mma.cta_group::2, M = 256 per MMA): neighbouring M tiles share the weight tile,
+                      // each CTA stages half of it.  Normal orientation only, BN % 32 == 0, split-K <= 4.
     unsigned long long* dbg_ts;  // optional per-CTA timeline (8 stamps per CTA)
     float* partial;   // unused since split-K moved into a cluster (kept for ABI stability; op-level entry: debug timeline)
     int* tile_counters;  // unused (ABI stability)
@@ -110,12 +112,13 @@ struct IgemmDesc {
 };
 
 struct IgemmPlan {
-    int mode;       // always 0 (igemm_kernel); kept for the plan-info ABI
+    int mode;       // 0 = igemm_kernel, 1 = igemm_pair_kernel (plan-info ABI)
     IgemmParams p;
     dim3 grid;
     size_t smem;
     int splits;
     long rows_total;
+    int pair;       // launched as igemm_pair_kernel with cluster dims (2, 1, splits)
 };
 
 // Returns 0 on success; fills plan. Encodes TMA descriptors (host side, no launch).

@@ -20,8 +20,8 @@ inline bool pdl_enabled() {
 }
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_z,
-                            Args&&... args) {
+inline cudaError_t launch_kc(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                             int cluster_z, Args&&... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -29,11 +29,11 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     int n = 0;
-    if (cluster_z > 1) {
+    if (cluster_z > 1 || cluster_x > 1) {
         attr[n].id = cudaLaunchAttributeClusterDimension;
-        attr[n].val.clusterDim.x = 1;
+        attr[n].val.clusterDim.x = (unsigned)(cluster_x > 1 ? cluster_x : 1);
         attr[n].val.clusterDim.y = 1;
-        attr[n].val.clusterDim.z = (unsigned)cluster_z;
+        attr[n].val.clusterDim.z = (unsigned)(cluster_z > 1 ? cluster_z : 1);
         ++n;
     }
     if (pdl_enabled()) {
@@ -46,6 +46,12 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
     if (e == cudaSuccess) e = cudaGetLastError();
     return e;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_z,
+                            Args&&... args) {
+    return launch_kc(kernel, grid, block, smem, stream, 1, cluster_z, static_cast<Args&&>(args)...);
 }
 
 }  // namespace b2

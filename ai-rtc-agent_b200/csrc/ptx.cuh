@@ -81,6 +81,40 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Cluster-scope variants for barriers that a peer CTA arrives on (CTA-pair MMA: operands-landed relay, accumulator-drained)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    uint64_t t0 = 0;
+    uint32_t spins = 0;
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if ((++spins & 0x3ff) == 0) {
+            const uint64_t now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > B2_WAIT_TIMEOUT_NS) {
+                printf("b2: cluster mbarrier wait timeout (block %d,%d,%d thread %d parity %u)\n", blockIdx.x,
+                       blockIdx.y, blockIdx.z, threadIdx.x, parity);
+                __trap();
+            }
+        }
+    }
+}
+
 // smem writes by normal (generic-proxy) stores -> visible to async proxy (TMA / UMMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -107,6 +141,11 @@ __device__ __forceinline__ uint32_t dsmem_map(uint32_t local_smem_addr, uint32_t
 }
 __device__ __forceinline__ void dsmem_st_f2(uint32_t cluster_addr, float x, float y) {
     asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_ld_u32(uint32_t cluster_addr) {
+    uint32_t v;
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(cluster_addr) : "memory");
+    return v;
 }
 __device__ __forceinline__ float4 dsmem_ld_f4(uint32_t cluster_addr) {
     float4 v;
@@ -169,6 +208,37 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         "}\n" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// CTA-pair form (cta_group::2): M = 256 over two CTAs of a cluster whose ranks differ in bit 0.  Each CTA holds its own 128 A
+// rows and HALF of the B tile (N/2 rows) at the same shared-memory offsets; the leader (even rank) issues, and the accumulator
+// rows [0,128) / [128,256) land in the leader's / the peer's tensor memory at the same address.  Per MMA the shared-memory
+// operand port of each SM then reads (128 + N/2) rows instead of (128 + N).
+__device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// ... its completion arrives on the barrier at this CTA-relative offset in every CTA of `cta_mask` (cluster ranks)
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
+// tensor-memory allocation of a CTA pair: one warp of EACH of the two CTAs issues it (collective)
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2cta() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 // Same, with the A operand read from tensor memory ("TS" form): lane i of the A region holds row i, 32-bit column j holds the
 // K elements (2j, 2j+1), so one K = 16 step consumes 8 columns.  Used by the attention kernel's P.V product: P never

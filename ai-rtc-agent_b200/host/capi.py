@@ -70,6 +70,7 @@ OUT_U8_NCHW, OUT_F16_NCHW = 0, 1
 IG_RELU = 1
 IG_GEGLU = 2
 IG_TCONV = 64
+IG_PAIR = 128
 
 _lib = None
 

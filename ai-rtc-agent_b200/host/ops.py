@@ -32,7 +32,7 @@ def igemm(srcs: Sequence[Tuple[torch.Tensor, int]], w: torch.Tensor, out: torch.
           stride: int = 1, colbias: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
           acc_scale: float = 1.0, res_scale: float = 1.0, relu: bool = False, geglu: bool = False,
           bn: int = 0, splits: int = 1, n_valid: Optional[int] = None, timeline: Optional[torch.Tensor] = None, swap: bool = False,
-          tconv: bool = False,
+          tconv: bool = False, pair: bool = False,
           rowstat_out: Optional[torch.Tensor] = None, rowstat_in: Optional[torch.Tensor] = None,
           colsum: Optional[torch.Tensor] = None, ln_c: int = 0, ln_eps: float = 1e-5,
           out2: Optional[torch.Tensor] = None, col2: int = 0) -> torch.Tensor:
@@ -62,7 +62,7 @@ def igemm(srcs: Sequence[Tuple[torch.Tensor, int]], w: torch.Tensor, out: torch.
         assert res.dtype == torch.float16
         d.res, d.ldr = res.data_ptr(), res.stride(2)
     d.acc_scale, d.res_scale = acc_scale, res_scale
-    d.flags = (capi.IG_RELU if relu else 0) | (capi.IG_GEGLU if geglu else 0) | (capi.IG_TCONV if tconv else 0)
+    d.flags = (capi.IG_RELU if relu else 0) | (capi.IG_GEGLU if geglu else 0) | (capi.IG_TCONV if tconv else 0) | (capi.IG_PAIR if pair else 0)
     if rowstat_out is not None:
         assert rowstat_out.dtype == torch.int64 and rowstat_out.is_contiguous()
         d.rowstat_out = rowstat_out.data_ptr()

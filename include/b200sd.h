@@ -40,7 +40,9 @@ typedef struct {
 enum {
     B2SD_IG_RELU = 1,
     B2SD_IG_GEGLU = 2,
-    B2SD_IG_TCONV = 64       /* run the persistent halo-tile kernel (stride-1 3x3, 64 -> 64 channels: the TAESD body) */
+    B2SD_IG_TCONV = 64,      /* run the persistent halo-tile kernel (stride-1 3x3, 64 -> 64 channels: the TAESD body) */
+    B2SD_IG_PAIR = 128       /* CTA pairs: tcgen05.mma.cta_group::2 (M = 256 per MMA), each CTA stages half of the weight tile;
+                                normal orientation, bn % 32 == 0, splits <= 4 */
 };
 
 /* conv3x3 / conv1x1 / Linear as one implicit GEMM:
@@ -90,7 +92,7 @@ int b2sd_op_igemm(const b2sd_igemm_desc* d, void* stream);
  * given) or the engine's tile policy (autotile = 1; allow_swap = the contraction may use the swapped orientation) would
  * launch for this contraction.  Pointers in the descriptor only need plausible alignment.  For tests of the host logic. */
 typedef struct {
-    int mode;          /* always 0 (igemm_kernel); the persistent halo-tile kernel is requested with B2SD_IG_TCONV */
+    int mode;          /* 0 = igemm_kernel, 1 = igemm_pair_kernel (CTA pairs); the halo-tile kernel is requested with B2SD_IG_TCONV */
     int swap, bn, splits;
     int grid_x, grid_y, grid_z;
     int num_stages;    /* operand ring depth */
