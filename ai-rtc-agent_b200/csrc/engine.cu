@@ -119,18 +119,27 @@ struct Op {
 // allow_swap: the caller is a UNet contraction (never TAESD / V^T / GEGLU).  Host-only: works in igemm dry-run mode.
 static int igemm_autotile_single(IgemmDesc d, bool allow_swap, IgemmPlan* plan_out);
 
-// Tile policy + CTA pairs: the single-CTA policy picks orientation, N tile and split-K; where the result has at least two M tiles
-// (normal orientation, N tile a multiple of 32, split-K <= 4) the same tiles are launched as CTA pairs (igemm_pair_kernel), which
-// halves the weight bytes every SM stages and reads per MMA.  B2_PAIR=0 switches the pairs off.
+// Tile policy + CTA pairs.  The single-CTA policy picks orientation, N tile and split-K.  With d.pair_auto (set by the engine
+// when several frames are in flight) a normal-orientation result with >= 2 M tiles and an N tile that is a multiple of 32 is
+// re-planned as CTA pairs (igemm_pair_kernel) with the same N tile and the split-K factor capped at d.pair_splits: under
+// concurrency the GPU is filled by the other frames, so what counts is SM time per contraction, and a pair stages half the
+// weight bytes per SM, has a deeper ring in the same shared memory and needs no cluster reduction (same-box A/B, 6 lanes:
+// 440.6 -> 470.5 frames/s; the same tiles WITHOUT pairing: 433.0; pairs with the latency policy's split-K: 417.6;
+// profiles/ab_r02u.txt, ab_r02x.txt).  Tuning overrides: B2_PAIR=0/1/2, B2_PAIR_SPLITS=n, B2_PAIR_SINGLE=1 (control: re-plan
+// with the capped split-K but single CTAs).
 int igemm_autotile(IgemmDesc d, bool allow_swap, IgemmPlan* plan_out) {
     TRY(igemm_autotile_single(d, allow_swap, plan_out));
     static const char* pair_env = getenv("B2_PAIR");
-    const int pair_mode = pair_env ? atoi(pair_env) : 0;
+    static const char* ps_env = getenv("B2_PAIR_SPLITS");
+    static const bool pair_single = getenv("B2_PAIR_SINGLE") != nullptr;
+    const int pair_mode = pair_env ? atoi(pair_env) : d.pair_auto;
+    const int pair_splits = ps_env ? atoi(ps_env) : (d.pair_splits > 0 ? d.pair_splits : 4);
     const IgemmPlan& pl = *plan_out;
     const int m_tiles = pl.p.tiles_w * pl.p.tiles_h * pl.p.tiles_n;
-    if (pair_mode <= 0 || pl.p.swap || m_tiles < 2 || (pl.p.BN % 32) != 0 || pl.splits > 4) return 0;
-    if (pair_mode == 2 && pl.p.total_kb < 20) return 0;   // K-heavy contractions only (the mainloop must dominate)
-    d.swap = 0; d.BN = pl.p.BN; d.splits = pl.splits; d.partial = nullptr; d.pair = 1;
+    if (pair_mode <= 0 || pl.p.swap || m_tiles < 2 || (pl.p.BN % 32) != 0) return 0;
+    if (pair_mode == 2 && pl.p.total_kb < 20) return 0;
+    d.swap = 0; d.BN = pl.p.BN; d.splits = pl.splits > pair_splits ? pair_splits : pl.splits; d.partial = nullptr;
+    d.pair = pair_single ? 0 : 1;
     IgemmPlan paired;
     if (igemm_plan(d, &paired)) return 0;   // keep the single-CTA plan
     *plan_out = paired;
@@ -480,6 +489,10 @@ struct b2sd_engine {
         if (concurrency > 1 && d.ring_kb == 0) d.ring_kb = 100;
         // ... and spreading one contraction over fewer K slices costs latency but less SM time (cluster reduction): +1.5 %
         if (concurrency > 1 && d.max_splits == 0) d.max_splits = 4;
+        // ... and with the GPU filled by >= 4 frames, CTA pairs without split-K use the least SM time per contraction
+        // (igemm_autotile): +6.8 % at 6 lanes, +11 % at 8.  Two stage-pipelined lanes of ONE stateful stream (T > 1) run mostly
+        // one UNet at a time and keep split-K: pairs there measured -14 % (SD-1.5 4-step 512^2, profiles/ab_sd15_r02z.txt).
+        if (concurrency >= 4 && d.pair_auto == 0) { d.pair_auto = 1; d.pair_splits = 1; }
         IgemmPlan plan;
         TRY(igemm_autotile(d, allow_swap && !extras, &plan));
         if (d.epi.out2 && d.epi.col2 % plan.p.BN != 0) {   // an N tile must be all q/k or all v (igemm_autotile filters on it)

@@ -188,7 +188,10 @@ __device__ __forceinline__ void igemm_body(const IgemmParams& p) {
         }
         fence_mbar_init();
     }
-    if (PAIR) cluster_sync_all();   // the peer's barriers exist before anything arrives on them; both CTAs are resident
+    if (PAIR) {   // the peer's barriers exist before anything arrives on them; both CTAs are resident (execution barrier only:
+        cluster_arrive_relaxed();   // the release/acquire form costs a MEMBAR.ALL.GPU + L1 invalidate)
+        cluster_wait();
+    }
     if (warp == 1) {
         if (PAIR) {
             tmem_alloc_2cta(tmem_slot, p.tmem_cols);
@@ -290,13 +293,12 @@ __device__ __forceinline__ void igemm_body(const IgemmParams& p) {
         for (int mt = mt_first; mt < num_mtiles; mt += mt_step, ++it) {
             const int buf = it & 1;
             // epilogue has drained this accumulator (pairs: both CTAs' epilogues arrive here)
-            if (PAIR) mbar_wait_cluster(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);
-            else mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);
+            mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)buf * acc_stride;
             for (int kb = kb_begin; kb < kb_end; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
-                if (PAIR) mbar_wait_cluster(&peer_full[stage], phase);
+                if (PAIR) mbar_wait(&peer_full[stage], phase);
                 tc_fence_after();
                 B2_TS(if (ts && it == 0 && kb == kb_begin && lane == 0) ts[3] = globaltimer_ns();)
                 const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
@@ -558,8 +560,12 @@ __device__ __forceinline__ void igemm_body(const IgemmParams& p) {
         cluster_sync_all();  // nobody may exit while a peer still reads its shared memory
     }
     tc_fence_before();
-    if (PAIR) cluster_sync_all();   // both CTAs are done with the pair's tensor memory and with each other's barriers
-    else __syncthreads();
+    if (PAIR) {   // both CTAs are done with the pair's tensor memory and with each other's barriers
+        cluster_arrive_relaxed();
+        cluster_wait();
+    } else {
+        __syncthreads();
+    }
     if (warp == 1) {
         if (PAIR) tmem_dealloc_2cta(tmem_base, p.tmem_cols);
         else tmem_dealloc(tmem_base, p.tmem_cols);

@@ -103,6 +103,8 @@ struct IgemmDesc {
     int splits;       // 0/1 = none
     int ring_kb;      // operand ring budget in KB, 0 = auto (200 when the launch has <= 1 CTA per SM, else 100)
     int max_splits;   // cap of the split-K factor chosen by igemm_autotile, 0 = 8
+    int pair_auto;    // igemm_autotile only: 0 = single CTAs, 1 = launch every eligible contraction as CTA pairs, 2 = only K >= 1280
+    int pair_splits;  // ... and cap the split-K factor of those paired launches (0 = 4); the N tile of the single-CTA policy is kept
     int pair;         // 1 = CTA pairs (tcgen05.mma.cta_group::2, M = 256 per MMA): neighbouring M tiles share the weight tile,
                       // each CTA stages half of it.  Normal orientation only, BN % 32 == 0, split-K <= 4.
     unsigned long long* dbg_ts;  // optional per-CTA timeline (8 stamps per CTA)

@@ -81,38 +81,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-// Cluster-scope variants for barriers that a peer CTA arrives on (CTA-pair MMA: operands-landed relay, accumulator-drained)
+// Arrive on a barrier in a peer CTA's shared memory (CTA-pair MMA: operands-landed relay, accumulator-drained).  Default
+// semantics on purpose: what crosses the pair is the ORDER of async-proxy work (TMA landed -> tcgen05.mma may read it; tcgen05.ld
+// retired -> the accumulator may be overwritten), not generic-proxy data, and the .release.cluster / .acquire.cluster forms
+// compile to MEMBAR.ALL.GPU + CCTL.IVALL per use (measured: +6 us per launch).
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait_cluster(bar, parity)) return;
-    uint64_t t0 = 0;
-    uint32_t spins = 0;
-    while (!mbar_try_wait_cluster(bar, parity)) {
-        if ((++spins & 0x3ff) == 0) {
-            const uint64_t now = globaltimer_ns();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > B2_WAIT_TIMEOUT_NS) {
-                printf("b2: cluster mbarrier wait timeout (block %d,%d,%d thread %d parity %u)\n", blockIdx.x,
-                       blockIdx.y, blockIdx.z, threadIdx.x, parity);
-                __trap();
-            }
-        }
-    }
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
 // smem writes by normal (generic-proxy) stores -> visible to async proxy (TMA / UMMA reads)

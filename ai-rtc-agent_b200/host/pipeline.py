@@ -25,7 +25,8 @@ DEFAULT_PROMPT = "fireworks in the night sky"
 DEFAULT_T_INDEX_LIST = [18, 26, 35, 45]
 DEFAULT_NUM_INFERENCE_STEPS = 50
 DEFAULT_GUIDANCE_SCALE = 0.0
-DEFAULT_LANES_ONE_STEP = 6    # frames in flight for a 1-step stream batch (measured: 1 -> 241, 2 -> 331, 4 -> 423, 6 -> 443, 8 -> 441 fps; p50 4.2 / 6.1 / 9.6 / 13.6 / 18.4 ms)
+DEFAULT_LANES_ONE_STEP = 8    # frames in flight for a 1-step stream batch (measured with the throughput launch policy: 4 -> 409, 6 -> 470,
+                              # 8 -> 483, 10 -> 481, 12 -> 486 fps; p50 submit -> result 10.4 / 13.5 / 16.8 / 17.8 / 18.7 ms; lanes=1: 241 fps, 4.2 ms)
 DEFAULT_LANES_STATEFUL = 2    # T > 1: stage pipelining over two lanes that share the stream-batch state
 
 
@@ -85,7 +86,9 @@ class StreamDiffusionPipeline:
             lanes = int(os.getenv("B200SD_LANES", "0")) or (DEFAULT_LANES_STATEFUL if stateful else DEFAULT_LANES_ONE_STEP)
         if stateful:
             lanes = min(lanes, 2)   # three stages, the middle one serial: a third lane has nothing to overlap
-        self.model.stream.set_concurrency(max(1, lanes))
+        # launch policy = number of frames in flight ($B200SD_POLICY_FRAMES overrides it for profiling: a single lane running the
+        # throughput policy's launches gives ncu a clean one-frame launch list)
+        self.model.stream.set_concurrency(max(1, int(os.environ.get("B200SD_POLICY_FRAMES", lanes))))
         self.model.prepare(prompt=self.prompt, num_inference_steps=DEFAULT_NUM_INFERENCE_STEPS,
                            guidance_scale=DEFAULT_GUIDANCE_SCALE)
         sd = self.model.stream

@@ -494,7 +494,7 @@ def main_gpu(args):
             tj = json.load(f)
         traffic, traffic_note = tj.get("dram_bytes_per_launch"), tj.get("note", "")
     roofline = {
-        "bound": "tensor", "kernel": "igemm_kernel (tcgen05 implicit-GEMM conv/linear)",
+        "bound": "tensor", "kernel": "igemm_kernel / igemm_pair_kernel (one source: tcgen05 implicit-GEMM conv/linear, single CTAs or cta_group::2 CTA pairs)",
         "achieved": ig_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
         "frac": ig_tflops / peaks["bf16_tflops_sustained"], "traffic": traffic,
         "peak_source": peak_src + ", sustained figure (kernel timed inside a long step)",
@@ -507,7 +507,9 @@ def main_gpu(args):
         "kernel_algorithmic_gflop_per_step": ig["flops"] / 1e9,
         "one_frame_at_a_time": {"achieved": ig_tflops_seq, "frac": ig_tflops_seq / peaks["bf16_tflops_sustained"],
                                 "kernel_ms_per_step": ig["ms"], "kernel_avg_launch_us": 1e3 * ig["ms"] / max(ig["launches"], 1),
-                                "note": "the same launches of ONE frame alone on the GPU (a dependent chain; round 1's figure)"},
+                                "note": "the same launches of ONE frame alone on the GPU, a dependent chain.  They are planned for the number of frames in flight "
+                                        "(>= 4: CTA pairs without split-K), so alone they are slower than a lanes=1 pipeline's latency plan "
+                                        "(single CTAs, cluster split-K: frac 0.18-0.20, DESIGN.md 4.7)"},
         "step_achieved": step_tflops, "step_frac": step_tflops / peaks["bf16_tflops_sustained"],
         "step_algorithmic_gflop": GFLOP_PER_FRAME,
         "other_kernels_in_graph": kinds,
@@ -534,7 +536,9 @@ def main_gpu(args):
         "config": bench_config(world),
         "frames_in_flight": lanes,
         "sequential": {"value": world * args.steps / (seq_ms / 1000.0), "unit": "frames/s", "ms_per_frame": seq_ms / args.steps,
-                       "note": "same frames through the blocking call, one frame on the GPU at a time (the reference's calling pattern)"},
+                       "note": "same frames through the blocking call, one frame on the GPU at a time (the reference's calling pattern), on THIS "
+                               "pipeline, whose launches are planned for its frames_in_flight; a lanes=1 pipeline plans for latency instead "
+                               "(SD-Turbo 512x512: 4.15 ms per frame, DESIGN.md 4.5)"},
         "p50_ms": p50,
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": H * W * 3, "d2h_bytes_per_step": H * W * 3,
                 "p50_ms": p50, "p99_ms": max(r[2] for r in per), "max_ms": max(r[3] for r in per), "slowest_rank": slowest,

@@ -251,7 +251,9 @@ int b2sd_launches_per_step(b2sd_handle h);
 int b2sd_share_stream_state(b2sd_handle lane, b2sd_handle owner);
 /* How many frames will be in flight on this GPU (lanes / independent streams).  1 (default): launch policy tuned for the
  * latency of a single frame; > 1: policy tuned for throughput (smaller operand rings so CTAs of different frames share an
- * SM).  Takes effect at the next b2sd_prepare. */
+ * SM; from 4 frames in flight on, contractions are launched as CTA pairs -- tcgen05.mma.cta_group::2 -- without split-K: least
+ * SM time per contraction).
+ * Takes effect at the next b2sd_prepare. */
 int b2sd_set_concurrency(b2sd_handle h, int frames_in_flight);
 
 #ifdef __cplusplus

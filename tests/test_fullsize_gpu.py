@@ -25,9 +25,11 @@ def _weights(turbo, full=True):
     return cfg, arch, ow.make_unet_weights(cfg), ow.make_taesd_weights(), ow.make_prompt_embeds(cfg.cross_attention_dim)
 
 
-def _engine(arch, usd, vsd, emb, tl, hw):
+def _engine(arch, usd, vsd, emb, tl, hw, frames_in_flight=1):
     from ai_rtc_agent_b200.host.stream import StreamDiffusion
     sd = StreamDiffusion(arch, usd, vsd, tl, lambda p: emb, width=hw, height=hw, device="cuda")
+    if frames_in_flight > 1:   # throughput launch policy: 100 KB operand rings, CTA pairs (igemm_pair_kernel) without split-K
+        sd.set_concurrency(frames_in_flight)
     sd.prepare("p", guidance_scale=0.0)
     return sd
 
@@ -66,17 +68,21 @@ def test_gpu_oracle_equals_cpu_oracle(cuda):
         assert rel < 1e-4 and d.max().item() <= 1 and (d == 0).float().mean().item() > 0.999, (i, rel, d.max().item())
 
 
-@pytest.mark.parametrize("turbo,tl,hw,nframes", [
-    (False, [18, 26, 35, 45], 512, 5),    # BASELINE config 3: SD-1.5 + LCM 4-step, the agent's default (lib/pipeline.py:12,23-36)
-    (False, [18, 26, 35, 45], 768, 4),    # config 5 shape: seq 9216, odd tile extents, whole-grid GroupNorm fallback
-    (True, [32], 512, 3),                 # config 2 (headline), against both library implementations
+@pytest.mark.parametrize("turbo,tl,hw,nframes,in_flight", [
+    (False, [18, 26, 35, 45], 512, 5, 1),    # BASELINE config 3: SD-1.5 + LCM 4-step, the agent's default (lib/pipeline.py:12,23-36)
+    (False, [18, 26, 35, 45], 768, 4, 1),    # config 5 shape: seq 9216, odd tile extents, whole-grid GroupNorm fallback
+    (True, [32], 512, 3, 1),                 # config 2 (headline), against both library implementations
+    (True, [32], 512, 3, 8),                 # ... under the throughput launch policy the default pipeline runs (CTA pairs)
+    (False, [18, 26, 35, 45], 512, 5, 2),    # config 3 under the policy of its two stage-pipelined lanes (100 KB rings, split-K <= 4)
+    (False, [18, 26, 35, 45], 512, 2, 4),    # ... and with CTA pairs on the SD-1.5 shapes (conv projections, head dims 40/80/160)
+    (False, [18, 26, 35, 45], 768, 2, 4),    # odd tile extents (odd M-tile counts: masked second tile of the last pair)
 ])
-def test_three_implementations_full_size(cuda, turbo, tl, hw, nframes):
+def test_three_implementations_full_size(cuda, turbo, tl, hw, nframes, in_flight):
     from oracle import pipeline as opipe
     from oracle import torch_gpu as tg
     from oracle import weights as ow
     cfg, arch, usd, vsd, emb = _weights(turbo)
-    sd = _engine(arch, usd, vsd, emb, tl, hw)
+    sd = _engine(arch, usd, vsd, emb, tl, hw, in_flight)
     ref32 = tg.build(cfg, usd, vsd, tl, hw, emb, sd.init_noise, torch.float32)
     ref16 = tg.build(cfg, usd, vsd, tl, hw, emb, sd.init_noise, torch.float16)
     for i in range(nframes):

@@ -38,7 +38,7 @@ def conv_case(nb, h, w, cin, cout, bn, splits, res=False, relu=False):
     fl = 2.0 * nb * h * w * cout * cin * 9
     print(f"conv {nb}x{h}x{w} {cin}->{cout} bn={bn} splits={splits}: {us:8.1f} us  {fl/us/1e6:7.1f} TF/s")
 
-def conv_cold(nb, h, w, cin, cout, bn, splits, swap, taps=9, res=True):
+def conv_cold(nb, h, w, cin, cout, bn, splits, swap, taps=9, res=True, pair=False):
     """weights rotate over > 2x L2 so every launch streams them from HBM like the real frame does"""
     wbytes = cout * cin * taps * 2
     ncopy = max(2, min(64, int(300e6 // wbytes) + 1))
@@ -50,15 +50,31 @@ def conv_cold(nb, h, w, cin, cout, bn, splits, swap, taps=9, res=True):
     it = [0]
     def fn():
         it[0] += 1
-        ops.igemm([(x, taps)], wts[it[0] % ncopy], y, colbias=b, bn=bn, splits=splits, res=r, swap=swap)
+        ops.igemm([(x, taps)], wts[it[0] % ncopy], y, colbias=b, bn=bn, splits=splits, res=r, swap=swap, pair=pair)
     us = timeit_graph(fn, 2 * ncopy)
     fl = 2.0 * nb * h * w * cout * cin * taps
-    print(f"{'swap' if swap else 'base'} taps={taps} {nb}x{h}x{w} {cin}->{cout} bn={bn} splits={splits}: {us:8.1f} us  {fl/us/1e6:7.1f} TF/s  {wbytes/us/1e3:7.1f} GB/s(w)", flush=True)
+    print(f"{'swap' if swap else ('pair' if pair else 'base')} taps={taps} {nb}x{h}x{w} {cin}->{cout} bn={bn} splits={splits}: {us:8.1f} us  {fl/us/1e6:7.1f} TF/s  {wbytes/us/1e3:7.1f} GB/s(w)", flush=True)
 if "gn" in sys.argv:
     for args in [(1, 64, 64, 320), (1, 64, 64, 640, 320), (1, 64, 64, 320, 320), (1, 32, 32, 640), (1, 32, 32, 1280, 640), (1, 16, 16, 1280), (1, 16, 16, 1280, 1280), (1, 8, 8, 1280, 1280), (4, 64, 64, 320)]:
         xa = rnd(*args[:4]); cb = args[4] if len(args) > 4 else 0; xb = rnd(args[0], args[1], args[2], cb) if cb else None
         c = args[3] + cb; g = torch.ones(c, device=dev); b = torch.zeros(c, device=dev); y = torch.empty(args[0], args[1], args[2], c, device=dev, dtype=torch.float16)
         print(f"groupnorm {args}: {timeit_graph(lambda: ops.groupnorm(xa, xb, g, b, y), 20):7.2f} us per launch (chain of 20 in a graph)", flush=True)
+    sys.exit(0)
+if "pairsweep" in sys.argv:
+    # CTA pairs (tcgen05.mma.cta_group::2) against the single-CTA kernel, same tile / split-K, weights streamed from HBM
+    print("B2_STAGE_KB =", os.environ.get("B2_STAGE_KB", "default"))
+    for (h, cin, cout, taps) in [(64, 320, 320, 9), (64, 640, 320, 9), (64, 960, 320, 9), (64, 320, 320, 1), (64, 320, 1280, 1), (64, 1280, 320, 1),
+                                 (32, 640, 640, 9), (32, 1280, 640, 9), (32, 1920, 640, 9), (32, 640, 640, 1), (32, 2560, 640, 1),
+                                 (16, 1280, 1280, 9), (16, 2560, 1280, 9), (16, 1280, 1280, 1), (16, 5120, 1280, 1)]:
+        mt = (h * h + 127) // 128
+        for bn in [64, 128, 160, 256]:
+            if cout % bn: continue
+            for sp in [1, 2, 4]:
+                ctas = mt * (cout // bn) * sp
+                if ctas > 600 or ctas < 32 or sp * 4 > cin * taps // 64: continue
+                for pair in (False, True):
+                    try: conv_cold(1, h, h, cin, cout, bn, sp, False, taps, pair=pair)
+                    except Exception as e: print("fail", h, cin, cout, bn, sp, pair, str(e)[:80])
     sys.exit(0)
 if "tilesweep" in sys.argv:
     print("B2_STAGE_KB =", os.environ.get("B2_STAGE_KB", "default"))
