@@ -98,6 +98,16 @@ class StreamDiffusionPipeline:
         self._lane_streams = [None] if len(self._engines) == 1 else [torch.cuda.Stream(sd.device) for _ in self._engines]
         self._lane_done = [None] * len(self._engines)     # completion event of the last frame given to each lane
         self._next_lane = 0
+        # Every frame's output is a fresh tensor allocated on its lane's stream (the caller owns it and may hold it across calls,
+        # SURVEY 8b "Ownership").  Give each lane stream's allocator pool a few output-sized blocks now: the first cudaMalloc a
+        # lane needed in the middle of a stream otherwise synchronises the device, i.e. stalls every frame in flight once
+        # (seen as a single 2x latency spike, 33 ms instead of 17 ms, some 50-80 frames into a run with 10 frames pending).
+        for st in self._lane_streams:
+            if st is not None:
+                with torch.cuda.stream(st):
+                    prime = [torch.empty((1, 3, self.model.height, self.model.width), dtype=torch.uint8, device=sd.device)
+                             for _ in range(4)]
+                    del prime
 
     @property
     def lanes(self) -> int:

@@ -387,37 +387,46 @@ def main_gpu(args):
     barrier()
     seq_ms = max(r[0] for r in gather([timed_device_loop(lambda i: (pipe(ring_dev[(warm + i) % 64]), None)[1])]))
     # ---- end to end through the public API with host buffers (e2e): every step copies its frame from pinned host memory and
-    # reads its result back into pinned host memory; up to `lanes` frames in flight; latency = submit -> result on the host
+    # reads its result back into pinned host memory; latency = submit -> result on the host.  Up to `lanes + 2` frames are
+    # pending: a frame whose input is still being uploaded or whose result is being downloaded does not occupy the GPU's compute
+    # lanes, so two more than `lanes` keep all of them busy (each lane runs its frames in submission order; outputs are fresh
+    # tensors, nothing is overwritten).
     d2h = torch.cuda.Stream(dev)
-    out_ring = [torch.empty((1, 3, H, W), dtype=torch.uint8).pin_memory() for _ in range(lanes + 1)]
+    pending_max = lanes + 2 if lanes > 1 else 1
+    out_ring = [torch.empty((1, 3, H, W), dtype=torch.uint8).pin_memory() for _ in range(pending_max + 1)]
+
+    in_ring = [torch.empty((1, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(pending_max + 1)]
 
     def e2e_submit(i):
+        # no allocation on this path: the upload lands in a preallocated device slot (free again once its frame has been
+        # retired), and the result tensor is kept alive until its download has completed instead of record_stream()ing it -- a
+        # cudaMalloc in the middle of the loop would drain every frame in flight (a 16 ms stall seen once with .to() + record_stream)
         t0 = time.perf_counter()
-        frame = ring_host[(warm + i) % 64].to(dev, non_blocking=True)
+        frame = in_ring[i % (pending_max + 1)]
+        frame.copy_(ring_host[(warm + i) % 64], non_blocking=True)
         tk = pipe.enqueue(frame)
         tk.wait(d2h)
         with torch.cuda.stream(d2h):
             res = tk.result(wait=False)
-            out_ring[i % (lanes + 1)].copy_(res, non_blocking=True)
-            res.record_stream(d2h)
+            out_ring[i % (pending_max + 1)].copy_(res, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(d2h)
-        return t0, ev
+        return t0, ev, res
 
     def e2e_run(n, lat):
         pend = collections.deque()
         for i in range(n):
             pend.append(e2e_submit(i))
-            while len(pend) >= lanes:      # at most `lanes` frames in flight: retire the oldest before submitting the next
-                t0, ev = pend.popleft()
+            while len(pend) >= pending_max:      # retire the oldest before submitting the next
+                t0, ev, _res = pend.popleft()
                 ev.synchronize()
                 lat.append((time.perf_counter() - t0) * 1000.0)
         while pend:
-            t0, ev = pend.popleft()
+            t0, ev, _res = pend.popleft()
             ev.synchronize()
             lat.append((time.perf_counter() - t0) * 1000.0)
 
-    e2e_run(3 * lanes, [])     # untimed: first use of the pinned rings / copy streams on this rank
+    e2e_run(6 * pending_max, [])     # untimed: first use of the pinned rings / copy streams on this rank
     lat = []
     barrier()
     t_all = time.perf_counter()
@@ -542,7 +551,7 @@ def main_gpu(args):
         "p50_ms": p50,
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": H * W * 3, "d2h_bytes_per_step": H * W * 3,
                 "p50_ms": p50, "p99_ms": max(r[2] for r in per), "max_ms": max(r[3] for r in per), "slowest_rank": slowest,
-                "samples_per_rank": args.steps,
+                "samples_per_rank": args.steps, "frames_pending_max": pending_max,
                 "tails_note": None if args.steps >= 100 else f"p99/max come from only {args.steps} samples per rank"},
         "per_rank": per_rank,
         "numa": {"pinned": numa is not None, "rank0": numa, "nodes_by_rank": [int(r[0]) for r in numa_all]},
