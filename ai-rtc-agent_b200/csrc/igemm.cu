@@ -914,7 +914,10 @@ int igemm_plan(const IgemmDesc& d, IgemmPlan* plan) {
         if (grid_x > m_tiles) grid_x = m_tiles;
         p.acc_bufs = 2;
     }
-    if (pair) grid_x = (grid_x + 1) & ~1;   // CTAs (2j, 2j+1) of x are a pair; an odd tile count leaves one masked tile
+    if (pair) {   // CTAs (2j, 2j+1) of x are a pair: an odd tile count leaves one masked tile; a persistent launch stays within
+        // the co-resident wave (round down)
+        grid_x = (p.acc_bufs == 2 && grid_x > 2) ? (grid_x & ~1) : ((grid_x + 1) & ~1);
+    }
     uint32_t cols = 32;
     while (cols < (uint32_t)(BN * p.acc_bufs)) cols <<= 1;
     p.tmem_cols = cols;

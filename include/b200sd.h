@@ -88,9 +88,9 @@ typedef struct {
 
 int b2sd_op_igemm(const b2sd_igemm_desc* d, void* stream);
 
-/* Host-only planning (no GPU, no driver call): what b2sd_op_igemm (autotile = 0: the descriptor's bn / splits / swap as
- * given) or the engine's tile policy (autotile = 1; allow_swap = the contraction may use the swapped orientation) would
- * launch for this contraction.  Pointers in the descriptor only need plausible alignment.  For tests of the host logic. */
+/* Host-only planning (no GPU, no driver call): what b2sd_op_igemm (autotile = 0: the descriptor's bn / splits / swap / flags as
+ * given) or the engine's tile policy (autotile = 1: latency policy of a single frame in flight; 2: throughput policy of >= 4
+ * frames in flight; allow_swap = the contraction may use the swapped orientation) would launch for this contraction.  Pointers in the descriptor only need plausible alignment.  For tests of the host logic. */
 typedef struct {
     int mode;          /* 0 = igemm_kernel, 1 = igemm_pair_kernel (CTA pairs); the halo-tile kernel is requested with B2SD_IG_TCONV */
     int swap, bn, splits;

@@ -42,10 +42,12 @@ def _plan(d, autotile=1, allow_swap=0):
     return info
 
 
-def _check(info, d, total_kb, geglu=False):
+def _check(info, d, total_kb, geglu=False, pairs_ok=False):
     n_gemm = d.n_valid * (2 if geglu else 1)
     rows = d.nb * d.ho * d.wo
-    assert info.mode == 0 and info.rows_total == rows and info.total_kb == total_kb
+    assert info.mode in ((0, 1) if pairs_ok else (0,)) and info.rows_total == rows and info.total_kb == total_kb
+    if info.mode == 1:   # CTA pairs: x = pairs of neighbouring M tiles, cluster (2, 1, splits) within the portable limit of 8
+        assert not info.swap and info.bn % 32 == 0 and info.splits in (1, 2, 4) and info.grid_x % 2 == 0 and info.m_tiles >= 2
     assert info.splits in (1, 2, 4, 8) and info.grid_z == info.splits
     assert info.kb_per_split * info.splits >= total_kb > info.kb_per_split * (info.splits - 1), "empty or missing K slice"
     assert 2 <= info.num_stages <= 8
@@ -62,7 +64,7 @@ def _check(info, d, total_kb, geglu=False):
         if info.acc_bufs == 2:   # persistent over M tiles
             assert info.grid_x * info.grid_y <= 296 < info.m_tiles * info.grid_y and info.grid_x <= info.m_tiles
         else:
-            assert info.grid_x == info.m_tiles
+            assert info.grid_x == (info.m_tiles + 1) // 2 * 2 if info.mode == 1 else info.grid_x == info.m_tiles
 
 
 def _unet_shapes(chs, nb, latent=64):
@@ -97,6 +99,50 @@ def test_autotile_invariants_over_the_frame_program(nb, latent):
         ctas = info.grid_x * info.grid_y * info.grid_z
         if ctas > 148:
             assert info.smem_bytes <= 114 * 1024, f"{ctas} CTAs need two per SM but a CTA takes {info.smem_bytes} B ({srcs}->{cout} @{r})"
+
+
+@pytest.mark.parametrize("nb,latent", [(1, 64), (4, 64), (4, 96)])
+def test_throughput_policy_invariants(nb, latent):
+    """autotile = 2: what the engine plans with >= 4 frames in flight (CTA pairs without split-K, 100 KB operand rings)"""
+    shapes = _unet_shapes([320, 640, 1280, 1280], nb, latent)
+    paired = 0
+    for (b, r, srcs, cout, stride, geglu, allow_swap) in shapes:
+        d, kb = _desc(b, r, r, srcs, cout, stride=stride, geglu=geglu)
+        info = _plan(d, 2, int(allow_swap))
+        _check(info, d, kb, geglu, pairs_ok=True)
+        single = _plan(d, 1, int(allow_swap))
+        if info.mode == 1:
+            paired += 1
+            assert info.splits == 1 and info.smem_bytes <= 114 * 1024, "two CTAs of different frames share an SM"
+            assert info.num_stages >= 2 and (info.bn != 160 or info.num_stages >= 3 or info.total_kb < 3)
+        else:
+            assert info.swap or info.m_tiles < 2 or info.bn % 32 != 0, "an eligible contraction was left on single CTAs"
+        del single
+    assert paired >= len(shapes) // 2
+
+
+def test_throughput_policy_is_pinned():
+    """Measured on B200 (profiles/ab_r02x.txt, ab_r02y.txt, pairsweep_100.txt); a change here needs a new measurement."""
+    def pol(r, srcs, cout, allow_swap=1, **kw):
+        d, _ = _desc(1, r, r, srcs, cout, **kw)
+        i = _plan(d, 2, allow_swap)
+        return (i.mode, i.bn, i.splits, i.swap, i.grid_x, i.grid_y, i.num_stages)
+    assert pol(64, [(320, 9)], 320) == (1, 160, 1, 0, 32, 2, 3)          # 26 KB stages: three fit the 100 KB ring (single CTAs: two)
+    assert pol(32, [(1280, 9)], 640)[:3] == (1, 160, 1)
+    assert pol(16, [(1280, 9)], 1280)[:6] == (1, 64, 1, 0, 2, 20)        # two M tiles = one pair per N tile, 180 K-blocks each
+    assert pol(8, [(1280, 9)], 1280)[:4] == (0, 64, 4, 1)                # one M tile: stays swapped, split-K capped at 4
+    assert pol(64, [(320, 1)], 1280, allow_swap=0, geglu=True)[:3] == (1, 256, 1)   # persistent pairs: 128 value + 128 gate rows per tile
+    explicit, _ = _desc(1, 64, 64, [(320, 9)], 320, bn=160, splits=4)
+    explicit.flags |= capi.IG_PAIR
+    i = _plan(explicit, 0)
+    assert (i.mode, i.grid_x, i.grid_y, i.grid_z) == (1, 32, 2, 4)
+    odd, _ = _desc(1, 24, 24, [(128, 9)], 64, bn=64)                     # 5 M tiles -> 3 pairs, the last one half masked
+    odd.flags |= capi.IG_PAIR
+    assert _plan(odd, 0).grid_x == 6
+    bad, _ = _desc(1, 64, 64, [(320, 9)], 320, bn=80)
+    bad.flags |= capi.IG_PAIR
+    info = capi.IgemmPlanInfo()
+    assert capi.lib().b2sd_igemm_plan_dry(C.byref(bad), 0, 0, C.byref(info)) != 0, "pairs need an N tile that is a multiple of 32"
 
 
 def test_autotile_random_sweep():
