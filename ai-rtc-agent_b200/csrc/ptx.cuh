@@ -116,11 +116,6 @@ __device__ __forceinline__ uint32_t dsmem_map(uint32_t local_smem_addr, uint32_t
 __device__ __forceinline__ void dsmem_st_f2(uint32_t cluster_addr, float x, float y) {
     asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(x), "f"(y) : "memory");
 }
-__device__ __forceinline__ uint32_t dsmem_ld_u32(uint32_t cluster_addr) {
-    uint32_t v;
-    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(cluster_addr) : "memory");
-    return v;
-}
 __device__ __forceinline__ float4 dsmem_ld_f4(uint32_t cluster_addr) {
     float4 v;
     asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
