@@ -387,12 +387,12 @@ def main_gpu(args):
     barrier()
     seq_ms = max(r[0] for r in gather([timed_device_loop(lambda i: (pipe(ring_dev[(warm + i) % 64]), None)[1])]))
     # ---- end to end through the public API with host buffers (e2e): every step copies its frame from pinned host memory and
-    # reads its result back into pinned host memory; latency = submit -> result on the host.  Up to `lanes + 2` frames are
-    # pending: a frame whose input is still being uploaded or whose result is being downloaded does not occupy the GPU's compute
-    # lanes, so two more than `lanes` keep all of them busy (each lane runs its frames in submission order; outputs are fresh
-    # tensors, nothing is overwritten).
+    # reads its result back into pinned host memory; latency = submit -> result on the host.  Up to `lanes` frames are pending
+    # (--e2e-pending): the next frame is submitted when the oldest has been retired, i.e. when its lane is free.  With lanes + 2
+    # pending the upload / download phases no longer cost a compute slot (+3 %: 484-488 frames/s instead of 470), but a frame
+    # can then queue behind a whole frame on its lane: p99 33 ms instead of 17.6 ms (profiles/bench_r02w_line.json).
     d2h = torch.cuda.Stream(dev)
-    pending_max = lanes + 2 if lanes > 1 else 1
+    pending_max = max(1, args.e2e_pending if args.e2e_pending > 0 else lanes)
     out_ring = [torch.empty((1, 3, H, W), dtype=torch.uint8).pin_memory() for _ in range(pending_max + 1)]
 
     in_ring = [torch.empty((1, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(pending_max + 1)]
@@ -577,6 +577,7 @@ if __name__ == "__main__":
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--no-numa-pin", action="store_true")
+    ap.add_argument("--e2e-pending", type=int, default=0, help="frames pending in the end-to-end loop (0 = frames_in_flight)")
     ap.add_argument("--workload", default="sd-turbo-512", choices=sorted(WORKLOADS))
     a = ap.parse_args()
     select_workload(a.workload)
